@@ -1,0 +1,420 @@
+#!/usr/bin/env python
+"""bench.py -- fused KNN + gather throughput of the FFB6D fusion hot path on B200.
+
+    python bench.py --gpus N --steps K --warmup W          (N>1: launched by torchrun)
+    python bench.py --impl reference ...                    (the reference's CPU ops, host cores)
+
+A *step* is one pass of the hot path over one batch of synthetic frames: the 22 KNN index
+builds of the dataset schedule + the 23 gathers of FFB6D.forward, B frames
+per GPU (default 32 = BASELINE.json configs[1]).  metric = points/sec = GPUs * B * N0 / t_pass.
+
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the step's xyz
+inputs come from pinned host memory (H2D inside the timed region) and a result digest is read
+back (D2H inside).  `roofline`: the dominant kernel, per-op CUDA events on the launching stream
+inside the timed region, against MEASURED_PEAKS.json.  `cpu_baseline`: the reference's compiled
+KNN (oracle/_ref, nanoflann, OpenMP over the batch) + its torch gather expression on the host
+cores, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "fused KNN+gather points/sec at 12288 pts"
+UNIT = "points/s"
+FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """nvidia-smi sampled every 200 ms while the GPU is under load (recipe's clocks line)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.lines = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "200",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()            # the exact process we started
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, pw = [], [], []
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+                pw.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "power_w_max": max(pw),
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# ------------------------------------------------------------------------------ CPU reference arm
+def _torch_cpu_random_sample(feature, pool_idx):
+    """The reference's torch expression (models/ffb6d.py:166-177) restated, on CPU threads."""
+    import torch
+    if feature.dim() > 3:
+        feature = feature.squeeze(3)
+    K, d, B = pool_idx.shape[-1], feature.shape[1], pool_idx.shape[0]
+    flat = pool_idx.reshape(B, -1)
+    g = torch.gather(feature, 2, flat.unsqueeze(1).repeat(1, d, 1)).contiguous()
+    return g.reshape(B, d, -1, K).max(dim=3, keepdim=True)[0]
+
+
+def cpu_reference_sample(n_points, frames_knn, frames_gather, reps=1):
+    """Time the reference's CPU implementation of one pass on a bounded sample.
+
+    KNN: the 22-call schedule on `frames_knn` stacked frames through the reference's compiled
+    cpp_knn_batch_omp (OpenMP over the batch = every thread the reference can use,
+    NN/knn_.cxx:108-109); falls back to the oracle port if oracle/_ref is absent.
+    Gathers: the 23 gathers of `frames_gather` frames with the reference's torch expression on
+    all host threads.  Returns dict(sec_per_frame, kind, cores, sample)."""
+    import numpy as np
+    import torch
+    from ffb6d_b200.synthetic import make_batch, image_pyramid_np
+    from ffb6d_b200.schedule import knn_schedule, gather_schedule
+    from oracle import ref_loader as R
+    from oracle import cpu_oracle as O
+
+    cores = os.cpu_count() or 1
+    kind = "reference" if R.knn_available() else "port"
+    batch = make_batch(range(1000, 1000 + frames_knn), n_points=n_points)
+    sets = {("cld", i): np.ascontiguousarray(batch["cld"][:, : n_points // 4 ** i]) for i in range(5)}
+    pyr = [image_pyramid_np(x) for x in batch["dpt_xyz"]]
+    for sr in (2, 4, 8):
+        sets[("img", sr)] = np.stack([p[sr] for p in pyr])
+    knn = (lambda s, q, k: R.knn_batch(s, q, k, omp=True)) if kind == "reference" else O.knn_batch
+    t_knn = 1e30
+    idx = {}
+    for _ in range(max(1, reps)):
+        t0 = time.perf_counter()
+        for key, s, q, k in knn_schedule(n_points):
+            idx[key] = knn(sets[s], sets[q], k).astype(np.int32)       # helper_tool.py:170
+        t_knn = min(t_knn, time.perf_counter() - t0)
+    # gathers
+    torch.set_num_threads(cores)
+    fg = min(frames_gather, frames_knn)
+    g = torch.Generator().manual_seed(0)
+    idx["choose"] = batch["choose"]
+    for i in range(4):
+        idx["cld_sub_idx%d" % i] = idx["cld_nei_idx%d" % i][:, : n_points // 4 ** (i + 1)]
+    ops_ = []
+    for op, key, C, S, Q, K in gather_schedule(n_points):
+        feat = torch.randn(fg, C, S, 1, generator=g)
+        ii = torch.from_numpy(np.ascontiguousarray(idx[key][:fg])).long()      # train_ycb.py:224-232
+        if op == "choose":
+            ii = ii.reshape(fg, -1, 1)
+        ops_.append((feat, ii))
+    t_g = 1e30
+    for _ in range(max(1, reps)):
+        t0 = time.perf_counter()
+        for feat, ii in ops_:
+            _torch_cpu_random_sample(feat, ii)
+        t_g = min(t_g, time.perf_counter() - t0)
+    sec_per_frame = t_knn / frames_knn + t_g / fg
+    sample = ("%d frames x 22 KNN calls via %s (OpenMP over the batch, %d threads), %.2f s; "
+              "%d frames x 23 gathers via the reference's torch expression on CPU (%d threads), %.2f s"
+              % (frames_knn, "oracle/_ref/libknn_ref.so (unmodified NN/knn_.cxx)" if kind == "reference"
+                 else "oracle port (brute force)", cores, t_knn, fg, cores, t_g))
+    return {"sec_per_frame": sec_per_frame, "kind": kind, "cores": cores, "sample": sample,
+            "t_knn": t_knn, "t_gather": t_g}
+
+
+def run_reference_arm(args, rank):
+    if rank != 0:
+        return 0
+    cores = os.cpu_count() or 1
+    fk = args.ref_frames or max(8, min(cores, 64))
+    for _ in range(args.warmup):
+        cpu_reference_sample(args.n_points, min(fk, 8), 1)
+    t0 = time.perf_counter()
+    per_frame = []
+    last = None
+    for _ in range(args.steps):
+        last = cpu_reference_sample(args.n_points, fk, 2, reps=2)
+        per_frame.append(last["sec_per_frame"])
+    wall = time.perf_counter() - t0
+    spf = sum(per_frame) / len(per_frame)
+    value = args.n_points / spf
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": spf * fk * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "FFB6D fusion pass: 22 KNN index builds + 23 gathers per frame, "
+                               "480x640 synthetic RGB-D, %d points, K=16" % args.n_points,
+                   "frames_per_step": fk, "note": "CPU arm: each step is a bounded sample of the workload"},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": last["cores"], "kind": last["kind"],
+                         "sample": last["sample"]},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "wall_s": wall,
+    }
+    print(json.dumps(line))
+    return 0
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as fh:
+            d = json.load(fh)
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def load_ncu_traffic():
+    """{kernel family: dram bytes per launch} from the committed ncu summary, if any."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "ncu_traffic.json")) as fh:
+            return json.load(fh)
+    except Exception:
+        return {}
+
+
+def kernel_family(op_name):
+    """Map a timed op to the kernel function that runs it."""
+    kind, key = op_name.split(":", 1)
+    if kind == "knn":
+        return "knn_k1" if ("interp" in key or key.startswith("p2r")) else "knn_k16"
+    return "gather_k1" if (key.startswith("p2r") or "interp" in key or key == "choose") else "gather_max_k16"
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="frames per GPU per step")
+    ap.add_argument("--n-points", type=int, default=12288)
+    ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"])
+    ap.add_argument("--ref-frames", type=int, default=0, help="frames per CPU-arm sample (0 = #cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--per-op", action="store_true", help="also print the per-op table to stderr")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    if args.impl == "reference":
+        return run_reference_arm(args, rank)
+
+    import numpy as np
+    import torch
+    import ffb6d_b200  # noqa: F401  (fails loudly if the CUDA library is missing)
+    from ffb6d_b200 import _lib
+    from ffb6d_b200.pipeline import FusionPass, OpTimer
+    from ffb6d_b200.synthetic import make_batch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product has no CPU path "
+                         "(use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    B, N0 = args.batch, args.n_points
+    # ---- synthetic inputs: distinct frames per rank, pinned on the host + resident on the device
+    batch = make_batch(range(rank * B, rank * B + B), n_points=N0)
+    cld_h = torch.from_numpy(batch["cld"]).pin_memory()
+    xyz_h = torch.from_numpy(batch["dpt_xyz"]).pin_memory()
+    cho_h = torch.from_numpy(batch["choose"]).pin_memory()
+    cld_d, xyz_d, cho_d = cld_h.to(dev), xyz_h.to(dev), cho_h.to(dev)
+    p = FusionPass(B, n_points=N0, device=dev, layout=args.layout, seed=rank)
+    feat_bytes = sum(f.numel() * 4 for f in p.features)
+
+    sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ
+                           else os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]) if rank == 0 else None
+
+    # ---- warm-up
+    for _ in range(args.warmup):
+        p(cld_d, xyz_d, cho_d)
+    torch.cuda.synchronize()
+
+    # ---- timed region 1: inputs resident in HBM, per-op events on the launching stream
+    timer = OpTimer()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0.record()
+    for _ in range(args.steps):
+        inputs, outs = p(cld_d, xyz_d, cho_d, timer)
+    e1.record()
+    torch.cuda.synchronize()
+    barrier()
+    launches = _lib.launch_count() - l0
+    ms = e0.elapsed_time(e1)
+
+    # ---- timed region 2: end to end (H2D of the step's xyz inputs, pass, D2H of a result digest)
+    digest_h = torch.empty((len(p.gathers) + 22) * 256, dtype=torch.float32).pin_memory()
+
+    def e2e_step():
+        c = cld_h.to(dev, non_blocking=True)
+        x = xyz_h.to(dev, non_blocking=True)
+        ch = cho_h.to(dev, non_blocking=True)
+        inp, out = p(c, x, ch)
+        parts = [o.reshape(-1)[:256] for o in out]
+        parts += [inp[k].reshape(-1)[:256].float() for k in sorted(inp) if "idx" in k and "sub" not in k]
+        d = torch.cat(parts)
+        digest_h[: d.numel()].copy_(d, non_blocking=True)
+        return d.numel()
+
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    f0.record()
+    for _ in range(args.steps):
+        ndig = e2e_step()
+    f1.record()
+    torch.cuda.synchronize()
+    e2e_wall_ms = (time.perf_counter() - t0) * 1e3
+    barrier()
+    e2e_ms = max(f0.elapsed_time(f1), e2e_wall_ms)
+    clocks = sampler.stop() if sampler is not None else None
+
+    # ---- max over ranks
+    if dist is not None:
+        tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms, e2e_ms = tt.tolist()
+        ll = torch.tensor([launches], device=dev, dtype=torch.int64)
+        dist.all_reduce(ll, op=dist.ReduceOp.SUM)
+        launches = int(ll.item())
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return 0
+
+    steps = args.steps
+    value = world * B * N0 * steps / (ms / 1e3)
+    e2e_value = world * B * N0 * steps / (e2e_ms / 1e3)
+    peak, peak_src = load_peaks()
+
+    # ---- roofline of the dominant kernel (per-op events, rank 0)
+    fam = {}
+    per_op = timer.summary()
+    for name, d in per_op.items():
+        f = fam.setdefault(kernel_family(name), {"ms": 0.0, "bytes": 0, "n": 0})
+        f["ms"] += d["ms"]
+        f["bytes"] += d["bytes"]
+        f["n"] += d["n"]
+    tot_ms = sum(f["ms"] for f in fam.values())
+    dom = max(fam, key=lambda k: fam[k]["ms"])
+    dd = fam[dom]
+    achieved = dd["bytes"] / (dd["ms"] / 1e3) / 1e9
+    traffic = load_ncu_traffic().get(dom)
+    roofline = {
+        "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "share_of_step": dd["ms"] / tot_ms, "launches_per_step": dd["n"] // steps,
+        "alg_bytes_per_launch": dd["bytes"] / dd["n"], "avg_launch_ms": dd["ms"] / dd["n"],
+        "families": {k: {"share": v["ms"] / tot_ms, "ms_per_step": v["ms"] / steps,
+                         "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in sorted(fam.items())},
+    }
+    pass_gbs = p.alg_bytes_per_frame * B * steps / (ms / 1e3) / 1e9
+    pass_roofline = {"alg_bytes_per_frame": p.alg_bytes_per_frame, "achieved": pass_gbs, "peak": peak,
+                     "unit": "GB/s", "frac": pass_gbs / peak,
+                     "note": "whole pass on one GPU: alg_bytes*B / t_pass / HBM peak (BASELINE.md §3)"}
+    if args.per_op:
+        for name, d in sorted(per_op.items(), key=lambda kv: -kv[1]["ms"]):
+            sys.stderr.write("%-28s %8.3f ms/step  %8.1f GB/s\n" % (
+                name, d["ms"] / steps, d["bytes"] / (d["ms"] / 1e3) / 1e9))
+
+    # ---- CPU baseline (rank 0, N=1 only): the reference's compiled ops on this box's cores
+    cpu_baseline = None
+    if world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        r = cpu_reference_sample(N0, args.ref_frames or max(8, min(cores, 64)), 2, reps=2)
+        cpu_baseline = {"value": N0 / r["sec_per_frame"], "unit": UNIT, "cores": r["cores"],
+                        "kind": r["kind"], "sample": r["sample"]}
+
+    h2d = cld_h.numel() * 4 + xyz_h.numel() * 4 + cho_h.numel() * 4
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": steps,
+        "warmup": args.warmup, "ms_per_step": ms / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {
+            "workload": "BASELINE configs[1]: batch=%d synthetic 480x640 RGB-D frames per GPU, %d sampled "
+                        "points, K=16; one pass = 22 KNN index builds + 11 random_sample + 11 "
+                        "nearest_interpolation + choose gather (BASELINE.md §3), fusion MLPs not included"
+                        % (B, N0),
+            "frames_per_gpu": B, "n_points": N0, "k": 16, "feature_layout": args.layout,
+            "parallelism": "frames sharded over %d GPU(s), no data-path collective" % world,
+            "l2": "per-step inputs (%.1f GB of features + xyz) exceed the 126 MB L2; no flush needed"
+                  % ((feat_bytes + h2d) / 1e9),
+        },
+        "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / steps,
+                "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": int(ndig) * 4,
+                "note": "H2D = cld + organised xyz + choose from pinned memory; D2H = 256-element digest of "
+                        "each of the 45 results; gather features are device-resident activations as in the "
+                        "reference (they are produced on the GPU by the network)"},
+        "gpu_launches": int(launches),
+        "roofline": roofline, "pass_roofline": pass_roofline,
+        "cpu_baseline": cpu_baseline, "clocks": clocks,
+    }
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,76 @@
+"""ctypes binding of libffb6d_b200.so (the C ABI declared in include/ffb6d_b200.h).
+
+There is no CPU fallback: if the shared library is missing or fails to load,
+importing this module raises, and every op in :mod:`ffb6d_b200.ops` fails with
+it.  Build it with ``python -c "import __graft_entry__ as g; g.build()"`` or
+``make -C ffb6d_b200/csrc``.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libffb6d_b200.so")
+
+OK = 0
+ERR_INVALID = -1
+ERR_CUDA = -2
+ERR_WORKSPACE = -3
+ERR_NO_DEVICE = -4
+LAYOUT_NCS = 0
+LAYOUT_NSC = 1
+MAX_K = 64
+
+
+class FFB6DError(RuntimeError):
+    """A libffb6d_b200 entry point returned a negative status."""
+
+    def __init__(self, code, msg):
+        super().__init__("libffb6d_b200 error %d: %s" % (code, msg))
+        self.code = code
+
+
+def _load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            "%s not found: the CUDA library has not been built (run __graft_entry__.build() "
+            "or `make -C ffb6d_b200/csrc`). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    vp, i64, sz, ci, fp = C.c_void_p, C.c_int64, C.c_size_t, C.c_int, C.c_float
+    sig = {
+        "ffb6d_version": (ci, []),
+        "ffb6d_last_error": (C.c_char_p, []),
+        "ffb6d_device_count": (ci, []),
+        "ffb6d_launch_count": (C.c_uint64, []),
+        "ffb6d_knn_workspace_bytes": (sz, [i64, i64, i64, ci]),
+        "ffb6d_knn_batch": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp]),
+        "ffb6d_knn_batch_algo": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, sz, ci, vp]),
+        "ffb6d_knn_batch_host": (ci, [vp, sz, sz, sz, vp, sz, sz, vp]),
+        "ffb6d_knn_host": (ci, [vp, sz, sz, vp, sz, sz, vp]),
+        "ffb6d_gather_max_fwd": (ci, [vp, vp, ci, i64, i64, i64, i64, ci, ci, vp, vp]),
+        "ffb6d_gather_max_bwd": (ci, [vp, vp, ci, vp, i64, i64, i64, i64, ci, ci, vp, vp]),
+        "ffb6d_gather_neighbour_fwd": (ci, [vp, vp, ci, i64, i64, i64, i64, ci, vp, vp]),
+        "ffb6d_gather_neighbour_bwd": (ci, [vp, vp, ci, i64, i64, i64, i64, ci, vp, vp]),
+        "ffb6d_relative_pos_encoding_fwd": (ci, [vp, vp, ci, i64, i64, ci, vp, vp]),
+        "ffb6d_grid_subsample_host": (ci, [vp, sz, vp, sz, vp, sz, fp, vp, vp, vp, C.POINTER(sz)]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib, sorted(sig)
+
+
+lib, SYMBOLS = _load()
+
+
+def last_error():
+    return lib.ffb6d_last_error().decode("utf-8", "replace")
+
+
+def check(rc):
+    if rc != OK:
+        raise FFB6DError(rc, last_error())
+
+
+def launch_count():
+    return int(lib.ffb6d_launch_count())

@@ -1,0 +1,508 @@
+// gather.cu -- gather + max-pool over neighbours, nearest-feature gather, neighbour
+// gather and relative position encoding (sm_100a).
+//
+// Reference ops (ffb6d/models/ffb6d.py:159-194, 309-312; models/RandLA/RandLANet.py:
+// 87-117, 216-234) are chains of reshape / repeat / torch.gather / max that
+// materialise an int64 [B,C,Q*K] index tensor and a [B,C,Q*K] feature tensor.  Here
+// every op is one kernel that reads each touched source row once and writes the
+// result once.
+//
+// NCS layout ([B,C,S], point axis contiguous -- the reference's NCHW):
+//   * "staged" kernel: a CTA copies CC whole channel rows (CC*S floats, coalesced
+//     128-bit loads) into shared memory, then its threads walk the queries: the K
+//     indices of a query are loaded once into registers and reused for all CC
+//     rows, neighbour values come from shared memory, the result row is written
+//     coalesced along q.  HBM traffic = rows once + idx (C/CC times, L2 hits) + out.
+//   * "direct" kernel for rows that do not fit shared memory (S > ~50k): same
+//     thread mapping, neighbour values through the read-only L1/L2 path.
+// NSC layout ([B,S,C], channel axis contiguous -- torch channels_last): a warp owns
+//   a query, lanes span channels with 128-bit loads: every neighbour is one
+//   contiguous row read (embedding-lookup pattern).
+#include "common.cuh"
+
+namespace ffb6d {
+
+// torch.max semantics: NaN propagates; first maximal element wins the arg-max
+__device__ __forceinline__ float max_nan(float m, float v) { return (v > m || v != v) ? v : m; }
+
+template <typename IdxT, int KT>
+__device__ __forceinline__ void load_ids(const IdxT *__restrict__ ip, int K, int (&id)[KT > 0 ? KT : 1])
+{
+    // K indices of one query are contiguous: 16 int32 = 64 B, 16 int64 = 128 B
+    if constexpr (KT > 0) {
+        if constexpr (sizeof(IdxT) == 4 && (KT % 4 == 0)) {
+            const int4 *p4 = reinterpret_cast<const int4 *>(ip);
+#pragma unroll
+            for (int k = 0; k < KT / 4; ++k) {
+                const int4 v = __ldg(p4 + k);
+                id[4 * k + 0] = v.x;
+                id[4 * k + 1] = v.y;
+                id[4 * k + 2] = v.z;
+                id[4 * k + 3] = v.w;
+            }
+        } else if constexpr (sizeof(IdxT) == 8 && (KT % 2 == 0)) {
+            const longlong2 *p2 = reinterpret_cast<const longlong2 *>(ip);
+#pragma unroll
+            for (int k = 0; k < KT / 2; ++k) {
+                const longlong2 v = __ldg(p2 + k);
+                id[2 * k + 0] = (int)v.x;
+                id[2 * k + 1] = (int)v.y;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) id[k] = (int)__ldg(ip + k);
+        }
+    }
+}
+
+// ------------------------------------------------------------------ NCS staged
+template <typename IdxT, int KT>
+__global__ void __launch_bounds__(256)
+gather_max_ncs_staged_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                             float *__restrict__ out, int C, int S, int Q, int K, int CC,
+                             int q_per_cta)
+{
+    extern __shared__ __align__(16) float rows[];  // [cc][S]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CC;
+    const int cc = min(CC, C - c0);
+    const float *src = feat + ((size_t)b * C + c0) * S;
+    const int n = cc * S;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(rows);
+        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
+    } else {
+        for (int t = threadIdx.x; t < n; t += blockDim.x) rows[t] = __ldg(src + t);
+    }
+    __syncthreads();
+
+    const int q0 = blockIdx.x * q_per_cta;
+    const int q1 = min(Q, q0 + q_per_cta);
+    float *dst = out + ((size_t)b * C + c0) * Q;
+    for (int q = q0 + threadIdx.x; q < q1; q += blockDim.x) {
+        const IdxT *ip = idx + ((size_t)b * Q + q) * K;
+        if constexpr (KT > 0) {
+            int id[KT];
+            load_ids<IdxT, KT>(ip, K, id);
+            for (int c = 0; c < cc; ++c) {
+                const float *r = rows + c * S;
+                float m = r[id[0]];
+#pragma unroll
+                for (int k = 1; k < KT; ++k) m = max_nan(m, r[id[k]]);
+                dst[(size_t)c * Q + q] = m;
+            }
+        } else {
+            for (int c = 0; c < cc; ++c) {
+                const float *r = rows + c * S;
+                float m = r[(int)__ldg(ip)];
+                for (int k = 1; k < K; ++k) m = max_nan(m, r[(int)__ldg(ip + k)]);
+                dst[(size_t)c * Q + q] = m;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------ NCS direct
+template <typename IdxT, int KT>
+__global__ void __launch_bounds__(256)
+gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                             float *__restrict__ out, int C, int S, int Q, int K, int CC)
+{
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CC;
+    const int cc = min(CC, C - c0);
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const float *src = feat + ((size_t)b * C + c0) * S;
+    float *dst = out + ((size_t)b * C + c0) * Q;
+    const IdxT *ip = idx + ((size_t)b * Q + q) * K;
+    if constexpr (KT > 0) {
+        int id[KT];
+        load_ids<IdxT, KT>(ip, K, id);
+        for (int c = 0; c < cc; ++c) {
+            const float *r = src + (size_t)c * S;
+            float v[KT];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) v[k] = __ldg(r + id[k]);
+            float m = v[0];
+#pragma unroll
+            for (int k = 1; k < KT; ++k) m = max_nan(m, v[k]);
+            dst[(size_t)c * Q + q] = m;
+        }
+    } else {
+        for (int c = 0; c < cc; ++c) {
+            const float *r = src + (size_t)c * S;
+            float m = __ldg(r + (int)__ldg(ip));
+            for (int k = 1; k < K; ++k) m = max_nan(m, __ldg(r + (int)__ldg(ip + k)));
+            dst[(size_t)c * Q + q] = m;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ NSC (channels last)
+// one warp per query; lane l handles channels 4l..4l+3 (+128 per pass)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather_max_nsc_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                      float *__restrict__ out, int C, int S, int Q, int K, long long total_q)
+{
+    const int lane = threadIdx.x & 31;
+    const long long w = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (w >= total_q) return;
+    const int b = (int)(w / Q);
+    const IdxT *ip = idx + (size_t)w * K;
+    const float *base = feat + (size_t)b * S * C;
+    float *o = out + (size_t)w * C;
+    // lanes fetch the indices once (K <= 64)
+    int my0 = (lane < K) ? (int)__ldg(ip + lane) : 0;
+    int my1 = (lane + 32 < K) ? (int)__ldg(ip + lane + 32) : 0;
+    if ((C & 3) == 0) {
+        for (int c = lane * 4; c < C; c += 128) {
+            float4 m = __ldg(reinterpret_cast<const float4 *>(base + (size_t)__shfl_sync(0xffffffffu, my0, 0) * C + c));
+            for (int k = 1; k < K; ++k) {
+                const int s = __shfl_sync(0xffffffffu, (k < 32) ? my0 : my1, k & 31);
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)s * C + c));
+                m.x = max_nan(m.x, v.x);
+                m.y = max_nan(m.y, v.y);
+                m.z = max_nan(m.z, v.z);
+                m.w = max_nan(m.w, v.w);
+            }
+            *reinterpret_cast<float4 *>(o + c) = m;
+        }
+    } else {
+        for (int c = lane; c < C; c += 32) {
+            float m = __ldg(base + (size_t)__shfl_sync(0xffffffffu, my0, 0) * C + c);
+            for (int k = 1; k < K; ++k) {
+                const int s = __shfl_sync(0xffffffffu, (k < 32) ? my0 : my1, k & 31);
+                m = max_nan(m, __ldg(base + (size_t)s * C + c));
+            }
+            o[c] = m;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ backward
+// grad_feat[b,c,argmax] += grad_out[b,c,q]; the arg-max is recomputed from feat
+// (first maximal k, NaN wins) so the forward stores nothing extra.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather_max_bwd_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                      const float *__restrict__ gout, float *__restrict__ gfeat, int C, int S,
+                      int Q, int K, int layout, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    int b, c, q;
+    size_t fs_c, fs_s;
+    if (layout == FFB6D_LAYOUT_NCS) {  // t = (b*C + c)*Q + q
+        q = (int)(t % Q);
+        c = (int)((t / Q) % C);
+        b = (int)(t / ((long long)Q * C));
+        fs_c = (size_t)S;
+        fs_s = 1;
+    } else {  // t = (b*Q + q)*C + c
+        c = (int)(t % C);
+        q = (int)((t / C) % Q);
+        b = (int)(t / ((long long)Q * C));
+        fs_c = 1;
+        fs_s = (size_t)C;
+    }
+    const float g = gout[t];
+    const IdxT *ip = idx + ((size_t)b * Q + q) * K;
+    const float *f = feat + (size_t)b * C * S + (size_t)c * fs_c;
+    int best = (int)__ldg(ip);
+    float m = __ldg(f + (size_t)best * fs_s);
+    for (int k = 1; k < K; ++k) {
+        const int s = (int)__ldg(ip + k);
+        const float v = __ldg(f + (size_t)s * fs_s);
+        if ((v > m || v != v) && !(m != m)) {
+            m = v;
+            best = s;
+        }
+    }
+    atomicAdd(gfeat + (size_t)b * C * S + (size_t)c * fs_c + (size_t)best * fs_s, g);
+}
+
+// ------------------------------------------------------------------ neighbour gather
+// out[b,n,k,:] = pc[b,idx[b,n,k],:]; one thread per output float (4 when D%4==0)
+template <typename IdxT, int VEC>
+__global__ void __launch_bounds__(256)
+gather_neighbour_kernel(const float *__restrict__ pc, const IdxT *__restrict__ idx,
+                        float *__restrict__ out, int S, int D, long long rows_per_b,
+                        long long total_vec)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total_vec) return;
+    const int dv = D / VEC;
+    const long long row = t / dv;  // (b*N + n)*K + k
+    const int j = (int)(t % dv) * VEC;
+    const int b = (int)(row / rows_per_b);
+    const int s = (int)__ldg(idx + row);
+    const float *src = pc + ((size_t)b * S + s) * D + j;
+    float *dst = out + (size_t)row * D + j;
+    if constexpr (VEC == 4) {
+        *reinterpret_cast<float4 *>(dst) = __ldg(reinterpret_cast<const float4 *>(src));
+    } else {
+        *dst = __ldg(src);
+    }
+}
+
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather_neighbour_bwd_kernel(const float *__restrict__ gout, const IdxT *__restrict__ idx,
+                            float *__restrict__ gpc, int S, int D, long long rows_per_b,
+                            long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const long long row = t / D;
+    const int j = (int)(t % D);
+    const int b = (int)(row / rows_per_b);
+    const int s = (int)__ldg(idx + row);
+    atomicAdd(gpc + ((size_t)b * S + s) * D + j, gout[t]);
+}
+
+// ------------------------------------------------------------------ relative position encoding
+// out[b,n,k,0..9] = [dist, dx,dy,dz, x_n,y_n,z_n, x_j,y_j,z_j]   (RandLANet.py:216-223)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+rel_pos_enc_kernel(const float *__restrict__ xyz, const IdxT *__restrict__ idx,
+                   float *__restrict__ out, int N, int K, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b*N+n)*K+k
+    if (t >= total) return;
+    const long long bn = t / K;
+    const int b = (int)(bn / N);
+    const int j = (int)__ldg(idx + t);
+    const float *pc = xyz + (size_t)bn * 3;
+    const float *pn = xyz + ((size_t)b * N + j) * 3;
+    const float cx = __ldg(pc), cy = __ldg(pc + 1), cz = __ldg(pc + 2);
+    const float nx = __ldg(pn), ny = __ldg(pn + 1), nz = __ldg(pn + 2);
+    const float dx = __fsub_rn(cx, nx), dy = __fsub_rn(cy, ny), dz = __fsub_rn(cz, nz);
+    const float ss = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    float *o = out + (size_t)t * 10;
+    o[0] = __fsqrt_rn(ss);
+    o[1] = dx;
+    o[2] = dy;
+    o[3] = dz;
+    o[4] = cx;
+    o[5] = cy;
+    o[6] = cz;
+    o[7] = nx;
+    o[8] = ny;
+    o[9] = nz;
+}
+
+// ------------------------------------------------------------------ host-side launch logic
+static int g_max_smem_optin = -1;
+static int max_smem_optin()
+{
+    if (g_max_smem_optin < 0) {
+        int dev = 0, v = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess ||
+            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+            cudaGetLastError();
+            v = 48 * 1024;
+        }
+        g_max_smem_optin = v;
+    }
+    return g_max_smem_optin;
+}
+
+template <typename IdxT, int KT>
+static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B, int64_t C,
+                      int64_t S, int64_t Q, int K, cudaStream_t st)
+{
+    const int smem_cap = max_smem_optin() - 1024;
+    const size_t row_bytes = (size_t)S * sizeof(float);
+    // rows that fit shared memory twice over (two CTAs per SM hide the staging latency)
+    const size_t budget = (size_t)smem_cap / 2;
+    if (row_bytes <= budget) {
+        int CC = (int)(budget / row_bytes);
+        if (CC > C) CC = (int)C;
+        // enough CTAs to fill the chip: split the channel range first, then the queries
+        const int64_t want = 2 * kNumSMs;
+        while (CC > 1 && B * ceil_div(C, CC) < want) CC = (CC + 1) / 2;
+        int64_t nq = 1;
+        const int64_t ctas = B * ceil_div(C, CC);
+        if (ctas < want) nq = ceil_div(want, ctas);
+        int64_t q_per_cta = ceil_div(Q, nq);
+        if (q_per_cta < 256) q_per_cta = 256;
+        nq = ceil_div(Q, q_per_cta);
+        const size_t smem = (size_t)CC * row_bytes;
+        auto kern = gather_max_ncs_staged_kernel<IdxT, KT>;
+        if (smem > 48 * 1024)
+            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)smem));
+        dim3 grid((unsigned)nq, (unsigned)ceil_div(C, CC), (unsigned)B);
+        kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, CC,
+                                      (int)q_per_cta);
+        FFB6D_LAUNCH_OK("gather_max_ncs_staged_kernel");
+    } else {
+        const int CC = 8;
+        dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, CC), (unsigned)B);
+        gather_max_ncs_direct_kernel<IdxT, KT>
+            <<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, CC);
+        FFB6D_LAUNCH_OK("gather_max_ncs_direct_kernel");
+    }
+    return FFB6D_OK;
+}
+
+template <typename IdxT>
+static int gather_max_fwd_t(const float *feat, const IdxT *idx, int64_t B, int64_t C, int64_t S,
+                            int64_t Q, int K, int layout, float *out, cudaStream_t st)
+{
+    if (layout == FFB6D_LAYOUT_NSC) {
+        const long long total_q = (long long)B * Q;
+        const int warps = 8;
+        gather_max_nsc_kernel<IdxT><<<(unsigned)ceil_div(total_q, warps), warps * 32, 0, st>>>(
+            feat, idx, out, (int)C, (int)S, (int)Q, K, total_q);
+        FFB6D_LAUNCH_OK("gather_max_nsc_kernel");
+        return FFB6D_OK;
+    }
+    const bool aligned = (reinterpret_cast<uintptr_t>(idx) & 15) == 0;
+    if (K == 1) return launch_ncs<IdxT, 1>(feat, idx, out, B, C, S, Q, K, st);
+    if (K == 8 && aligned) return launch_ncs<IdxT, 8>(feat, idx, out, B, C, S, Q, K, st);
+    if (K == 16 && aligned) return launch_ncs<IdxT, 16>(feat, idx, out, B, C, S, Q, K, st);
+    if (K == 32 && aligned) return launch_ncs<IdxT, 32>(feat, idx, out, B, C, S, Q, K, st);
+    return launch_ncs<IdxT, 0>(feat, idx, out, B, C, S, Q, K, st);
+}
+
+}  // namespace ffb6d
+
+using namespace ffb6d;
+
+extern "C" {
+
+int ffb6d_gather_max_fwd(const float *feat, const void *idx, int idx_is_i64, int64_t B, int64_t C,
+                         int64_t S, int64_t Q, int K, int layout, float *out,
+                         ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && C >= 0 && S >= 0 && Q >= 0, "gather_max_fwd: negative size");
+    FFB6D_CHECK_ARG(K >= 1 && K <= FFB6D_MAX_K, "gather_max_fwd: K=%d outside [1,%d]", K,
+                    FFB6D_MAX_K);
+    FFB6D_CHECK_ARG(layout == FFB6D_LAYOUT_NCS || layout == FFB6D_LAYOUT_NSC,
+                    "gather_max_fwd: unknown layout %d", layout);
+    FFB6D_CHECK_ARG(S < (1ll << 31) && Q < (1ll << 31) && C < (1ll << 31) && B < 65536 &&
+                        C <= 65535ll * 8,
+                    "gather_max_fwd: size too large");
+    if (B == 0 || C == 0 || Q == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(S > 0, "gather_max_fwd: empty source with non-empty index");
+    FFB6D_CHECK_ARG(feat && idx && out, "gather_max_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (idx_is_i64)
+        return gather_max_fwd_t<long long>(feat, (const long long *)idx, B, C, S, Q, K, layout, out, st);
+    return gather_max_fwd_t<int>(feat, (const int *)idx, B, C, S, Q, K, layout, out, st);
+}
+
+int ffb6d_gather_max_bwd(const float *feat, const void *idx, int idx_is_i64, const float *grad_out,
+                         int64_t B, int64_t C, int64_t S, int64_t Q, int K, int layout,
+                         float *grad_feat, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && C >= 0 && S >= 0 && Q >= 0, "gather_max_bwd: negative size");
+    FFB6D_CHECK_ARG(K >= 1 && K <= FFB6D_MAX_K, "gather_max_bwd: K=%d outside [1,%d]", K,
+                    FFB6D_MAX_K);
+    FFB6D_CHECK_ARG(layout == FFB6D_LAYOUT_NCS || layout == FFB6D_LAYOUT_NSC,
+                    "gather_max_bwd: unknown layout %d", layout);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B * C * S > 0) {
+        FFB6D_CHECK_ARG(grad_feat, "gather_max_bwd: null grad_feat");
+        FFB6D_CUDA(cudaMemsetAsync(grad_feat, 0, (size_t)B * C * S * sizeof(float), st));
+    }
+    if (B == 0 || C == 0 || Q == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(S > 0, "gather_max_bwd: empty source with non-empty index");
+    FFB6D_CHECK_ARG(feat && idx && grad_out, "gather_max_bwd: null pointer");
+    const long long total = (long long)B * C * Q;
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    if (idx_is_i64)
+        gather_max_bwd_kernel<long long><<<blocks, 256, 0, st>>>(
+            feat, (const long long *)idx, grad_out, grad_feat, (int)C, (int)S, (int)Q, K, layout, total);
+    else
+        gather_max_bwd_kernel<int><<<blocks, 256, 0, st>>>(feat, (const int *)idx, grad_out, grad_feat,
+                                                          (int)C, (int)S, (int)Q, K, layout, total);
+    FFB6D_LAUNCH_OK("gather_max_bwd_kernel");
+    return FFB6D_OK;
+}
+
+int ffb6d_gather_neighbour_fwd(const float *pc, const void *idx, int idx_is_i64, int64_t B,
+                               int64_t S, int64_t D, int64_t N, int K, float *out,
+                               ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && S >= 0 && D >= 0 && N >= 0 && K >= 0,
+                    "gather_neighbour_fwd: negative size");
+    if (B == 0 || D == 0 || N == 0 || K == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(S > 0, "gather_neighbour_fwd: empty source with non-empty index");
+    FFB6D_CHECK_ARG(pc && idx && out, "gather_neighbour_fwd: null pointer");
+    FFB6D_CHECK_ARG(S < (1ll << 31) && D < (1ll << 31), "gather_neighbour_fwd: size too large");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long rows_per_b = (long long)N * K;
+    const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(pc) & 15) == 0) &&
+                    ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+    const long long total = (long long)B * rows_per_b * (v4 ? D / 4 : D);
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    if (idx_is_i64) {
+        if (v4)
+            gather_neighbour_kernel<long long, 4><<<blocks, 256, 0, st>>>(
+                pc, (const long long *)idx, out, (int)S, (int)D, rows_per_b, total);
+        else
+            gather_neighbour_kernel<long long, 1><<<blocks, 256, 0, st>>>(
+                pc, (const long long *)idx, out, (int)S, (int)D, rows_per_b, total);
+    } else {
+        if (v4)
+            gather_neighbour_kernel<int, 4><<<blocks, 256, 0, st>>>(pc, (const int *)idx, out, (int)S,
+                                                                   (int)D, rows_per_b, total);
+        else
+            gather_neighbour_kernel<int, 1><<<blocks, 256, 0, st>>>(pc, (const int *)idx, out, (int)S,
+                                                                   (int)D, rows_per_b, total);
+    }
+    FFB6D_LAUNCH_OK("gather_neighbour_kernel");
+    return FFB6D_OK;
+}
+
+int ffb6d_gather_neighbour_bwd(const float *grad_out, const void *idx, int idx_is_i64, int64_t B,
+                               int64_t S, int64_t D, int64_t N, int K, float *grad_pc,
+                               ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && S >= 0 && D >= 0 && N >= 0 && K >= 0,
+                    "gather_neighbour_bwd: negative size");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (B * S * D > 0) {
+        FFB6D_CHECK_ARG(grad_pc, "gather_neighbour_bwd: null grad_pc");
+        FFB6D_CUDA(cudaMemsetAsync(grad_pc, 0, (size_t)B * S * D * sizeof(float), st));
+    }
+    if (B == 0 || D == 0 || N == 0 || K == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(S > 0, "gather_neighbour_bwd: empty source with non-empty index");
+    FFB6D_CHECK_ARG(grad_out && idx, "gather_neighbour_bwd: null pointer");
+    const long long rows_per_b = (long long)N * K;
+    const long long total = (long long)B * rows_per_b * D;
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    if (idx_is_i64)
+        gather_neighbour_bwd_kernel<long long><<<blocks, 256, 0, st>>>(
+            grad_out, (const long long *)idx, grad_pc, (int)S, (int)D, rows_per_b, total);
+    else
+        gather_neighbour_bwd_kernel<int><<<blocks, 256, 0, st>>>(grad_out, (const int *)idx, grad_pc,
+                                                                (int)S, (int)D, rows_per_b, total);
+    FFB6D_LAUNCH_OK("gather_neighbour_bwd_kernel");
+    return FFB6D_OK;
+}
+
+int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_is_i64, int64_t B,
+                                    int64_t N, int K, float *out, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && N >= 0 && K >= 0, "relative_pos_encoding_fwd: negative size");
+    if (B == 0 || N == 0 || K == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(xyz && idx && out, "relative_pos_encoding_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)B * N * K;
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    if (idx_is_i64)
+        rel_pos_enc_kernel<long long><<<blocks, 256, 0, st>>>(xyz, (const long long *)idx, out, (int)N,
+                                                             K, total);
+    else
+        rel_pos_enc_kernel<int><<<blocks, 256, 0, st>>>(xyz, (const int *)idx, out, (int)N, K, total);
+    FFB6D_LAUNCH_OK("rel_pos_enc_kernel");
+    return FFB6D_OK;
+}
+
+}  // extern "C"

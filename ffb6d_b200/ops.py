@@ -1,0 +1,318 @@
+"""Host-side mirror of the reference's op surface for the fusion hot path.
+
+Same function names, argument meaning and result shapes/dtypes as the reference
+(ethnhe/FFB6D); every call goes through the C ABI of libffb6d_b200.so
+(include/ffb6d_b200.h).  torch is used for device memory and streams only.
+No op has a CPU implementation: numpy inputs are copied to the GPU by the
+``*_host`` entry points, torch inputs must already be CUDA tensors.
+"""
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import lib, check, LAYOUT_NCS, LAYOUT_NSC
+
+_I64 = (torch.int64,)
+_IDX = (torch.int32, torch.int64)
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _need_cuda(t, name):
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor, got %r" % (name, type(t)))
+    if not t.is_cuda:
+        raise RuntimeError("%s must be a CUDA tensor: ffb6d_b200 has no CPU path" % name)
+
+
+def _idx_arg(idx, name):
+    if idx.dtype not in _IDX:
+        raise TypeError("%s must be int32 or int64, got %s" % (name, idx.dtype))
+    return idx.contiguous(), int(idx.dtype == torch.int64)
+
+
+# --------------------------------------------------------------------------- KNN
+def knn_search(support_pts, query_pts, k, out_dtype=None, algo=0):
+    """Exact KNN index build; mirrors ``DataProcessing.knn_search``
+    (models/RandLA/helper_tool.py:160-170).
+
+    :param support_pts: points you have, B*N1*3 (float32)
+    :param query_pts: points you want the neighbour indices of, B*N2*3
+    :param k: number of neighbours
+    :return: neighbour indices B*N2*k, ascending distance.
+
+    numpy in -> numpy int32 out, exactly as the reference (which casts the int64
+    result of ``nearest_neighbors.knn_batch`` with ``.astype(np.int32)``); the call
+    goes through ``ffb6d_knn_batch_host`` whose signature is that of the
+    reference's ``cpp_knn_batch_omp`` (NN/knn_.h:14-16).
+    CUDA tensors in -> CUDA tensor out (int32 unless ``out_dtype`` says int64), no
+    host round trip.
+    """
+    k = int(k)
+    if isinstance(support_pts, np.ndarray) or isinstance(query_pts, np.ndarray):
+        sup = np.ascontiguousarray(support_pts, dtype=np.float32)  # NN/knn.pyx:95-96
+        qry = np.ascontiguousarray(query_pts, dtype=np.float32)
+        if sup.ndim != 3 or qry.ndim != 3 or sup.shape[0] != qry.shape[0]:
+            raise ValueError("knn_search expects [B,N1,3] and [B,N2,3], got %s and %s"
+                             % (sup.shape, qry.shape))
+        B, S, dim = sup.shape
+        Q = qry.shape[1]
+        indices = np.zeros((B, Q, k), dtype=np.int64)               # NN/knn.pyx:93
+        check(lib.ffb6d_knn_batch_host(sup.ctypes.data, B, S, dim, qry.ctypes.data, Q, k,
+                                       indices.ctypes.data))
+        return indices.astype(np.int32)                             # helper_tool.py:170
+    _need_cuda(support_pts, "support_pts")
+    _need_cuda(query_pts, "query_pts")
+    sup = support_pts.contiguous().float()
+    qry = query_pts.contiguous().float()
+    if sup.dim() != 3 or qry.dim() != 3 or sup.shape[0] != qry.shape[0] or sup.shape[2] != 3 \
+            or qry.shape[2] != 3:
+        raise ValueError("knn_search expects [B,N1,3] and [B,N2,3], got %s and %s"
+                         % (tuple(sup.shape), tuple(qry.shape)))
+    B, S, _ = sup.shape
+    Q = qry.shape[1]
+    dt = torch.int32 if out_dtype is None else out_dtype
+    if dt not in _IDX:
+        raise TypeError("out_dtype must be torch.int32 or torch.int64")
+    out = torch.empty((B, Q, k), dtype=dt, device=sup.device)
+    with torch.cuda.device(sup.device):
+        ws_bytes = int(lib.ffb6d_knn_workspace_bytes(B, S, Q, k)) if algo != 1 else 0
+        ws = torch.empty(ws_bytes, dtype=torch.uint8, device=sup.device) if ws_bytes else None
+        check(lib.ffb6d_knn_batch_algo(sup.data_ptr(), qry.data_ptr(), B, S, Q, k, out.data_ptr(),
+                                       int(dt == torch.int64), ws.data_ptr() if ws is not None else None,
+                                       ws_bytes, int(algo), _stream(sup.device)))
+    return out
+
+
+# --------------------------------------------------------------------------- gather + max
+def _layout_of(f3):
+    """f3: [B,C,S] view.  Returns (tensor, layout) with tensor dense in that layout."""
+    B, Cc, S = f3.shape
+    sb, sc, ss = f3.stride()
+    if f3.is_contiguous():
+        return f3, LAYOUT_NCS
+    if S > 1 and Cc > 1 and sc == 1 and ss == Cc and (B == 1 or sb == Cc * S):
+        return f3, LAYOUT_NSC          # channels_last view of an NCHW tensor
+    return f3.contiguous(), LAYOUT_NCS
+
+
+class _GatherMax(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, f3, idx):
+        f3, layout = _layout_of(f3)
+        idx_c, i64 = _idx_arg(idx, "index")
+        B, Cc, S = f3.shape
+        Q, K = idx_c.shape[1], idx_c.shape[2]
+        if layout == LAYOUT_NCS:
+            out = torch.empty((B, Cc, Q), dtype=torch.float32, device=f3.device)
+        else:
+            out = torch.empty((B, Q, Cc), dtype=torch.float32, device=f3.device).transpose(1, 2)
+        with torch.cuda.device(f3.device):
+            check(lib.ffb6d_gather_max_fwd(f3.data_ptr(), idx_c.data_ptr(), i64, B, Cc, S, Q, K,
+                                           layout, out.data_ptr(), _stream(f3.device)))
+        ctx.save_for_backward(f3, idx_c)
+        ctx.layout = layout
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        f3, idx_c = ctx.saved_tensors
+        layout = ctx.layout
+        B, Cc, S = f3.shape
+        Q, K = idx_c.shape[1], idx_c.shape[2]
+        if layout == LAYOUT_NCS:
+            g = gout.contiguous()
+            gf = torch.empty((B, Cc, S), dtype=torch.float32, device=f3.device)
+        else:
+            g = gout.transpose(1, 2).contiguous().transpose(1, 2)   # dense [B,Q,C] storage
+            gf = torch.empty((B, S, Cc), dtype=torch.float32, device=f3.device).transpose(1, 2)
+        with torch.cuda.device(f3.device):
+            check(lib.ffb6d_gather_max_bwd(f3.data_ptr(), idx_c.data_ptr(),
+                                           int(idx_c.dtype == torch.int64), g.data_ptr(), B, Cc, S,
+                                           Q, K, layout, gf.data_ptr(), _stream(f3.device)))
+        return gf, None
+
+
+def _gather_max(feature, idx3):
+    """feature [B,C,S] or [B,C,S,1] f32 CUDA; idx3 [B,Q,K] -> [B,C,Q] (layout follows input)."""
+    _need_cuda(feature, "feature")
+    _need_cuda(idx3, "index")
+    if feature.dtype != torch.float32:
+        raise TypeError("feature must be float32 (the reference runs amp O0), got %s" % feature.dtype)
+    if feature.dim() == 4:
+        if feature.shape[3] != 1:
+            raise ValueError("feature must be [B,C,N,1], got %s" % (tuple(feature.shape),))
+        f3 = feature.squeeze(3)
+    elif feature.dim() == 3:
+        f3 = feature
+    else:
+        raise ValueError("feature must be [B,C,N] or [B,C,N,1], got %s" % (tuple(feature.shape),))
+    if idx3.dim() != 3 or idx3.shape[0] != f3.shape[0]:
+        raise ValueError("index must be [B,N',K] with the batch of feature, got %s"
+                         % (tuple(idx3.shape),))
+    if idx3.shape[2] < 1 or idx3.shape[2] > _lib.MAX_K:
+        raise ValueError("neighbour count %d outside [1,%d]" % (idx3.shape[2], _lib.MAX_K))
+    return _GatherMax.apply(f3, idx3)
+
+
+def random_sample(feature, pool_idx):
+    """Gather the K neighbours' features and max-pool over K; mirrors
+    ``FFB6D.random_sample`` (models/ffb6d.py:159-177) and ``Network.random_sample``
+    (models/RandLA/RandLANet.py:87-102).
+
+    :param feature: [B, d, N, 1] (or [B, d, N]) input features
+    :param pool_idx: [B, N', max_num] neighbour indices, N' the positions kept after pooling
+    :return: pool_features = [B, d, N', 1]
+    """
+    return _gather_max(feature, pool_idx).unsqueeze(3)
+
+
+def nearest_interpolation(feature, interp_idx):
+    """Nearest-neighbour feature interpolation (K = 1 gather); mirrors
+    ``FFB6D.nearest_interpolation`` (models/ffb6d.py:179-194) and the RandLA twin
+    (models/RandLA/RandLANet.py:104-117).
+
+    :param feature: [B, d, N, 1] input features
+    :param interp_idx: [B, up_num_points, 1] nearest neighbour index
+    :return: [B, d, up_num_points, 1] interpolated features
+    """
+    if feature.dim() != 4:
+        raise ValueError("feature must be [B,C,N,1], got %s" % (tuple(feature.shape),))
+    B, up = interp_idx.shape[0], interp_idx.shape[1]
+    return _gather_max(feature, interp_idx.reshape(B, up, 1)).unsqueeze(3)
+
+
+def choose_gather(rgb_emb, choose):
+    """The final ``choose`` gather of ``FFB6D.forward`` (models/ffb6d.py:309-312):
+    ``rgb_emb [B,C,H,W]`` (or [B,C,HW]), ``choose [B,1,N]`` -> ``[B,C,N]``."""
+    B, Cc = rgb_emb.shape[0], rgb_emb.shape[1]
+    f3 = rgb_emb.reshape(B, Cc, -1) if rgb_emb.dim() == 4 and rgb_emb.is_contiguous() else \
+        rgb_emb.flatten(2)
+    return _gather_max(f3, choose.reshape(B, -1, 1))
+
+
+# --------------------------------------------------------------------------- neighbour gather
+class _GatherNeighbour(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, pc, idx):
+        pc = pc.contiguous()
+        idx_c, i64 = _idx_arg(idx, "neighbor_idx")
+        B, S, D = pc.shape
+        N, K = idx_c.shape[1], idx_c.shape[2]
+        out = torch.empty((B, N, K, D), dtype=torch.float32, device=pc.device)
+        with torch.cuda.device(pc.device):
+            check(lib.ffb6d_gather_neighbour_fwd(pc.data_ptr(), idx_c.data_ptr(), i64, B, S, D, N, K,
+                                                 out.data_ptr(), _stream(pc.device)))
+        ctx.save_for_backward(idx_c)
+        ctx.shape = (B, S, D)
+        return out
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gout):
+        (idx_c,) = ctx.saved_tensors
+        B, S, D = ctx.shape
+        N, K = idx_c.shape[1], idx_c.shape[2]
+        g = gout.contiguous()
+        gpc = torch.empty((B, S, D), dtype=torch.float32, device=g.device)
+        with torch.cuda.device(g.device):
+            check(lib.ffb6d_gather_neighbour_bwd(g.data_ptr(), idx_c.data_ptr(),
+                                                 int(idx_c.dtype == torch.int64), B, S, D, N, K,
+                                                 gpc.data_ptr(), _stream(g.device)))
+        return gpc, None
+
+
+def gather_neighbour(pc, neighbor_idx):
+    """Gather the coordinates or features of neighbouring points; mirrors
+    ``Building_block.gather_neighbour`` (models/RandLA/RandLANet.py:225-234).
+
+    :param pc: [B, npoint, channel]
+    :param neighbor_idx: [B, npoint, nsamples]
+    :return: [B, npoint, nsamples, channel]
+    """
+    _need_cuda(pc, "pc")
+    _need_cuda(neighbor_idx, "neighbor_idx")
+    if pc.dtype != torch.float32:
+        raise TypeError("pc must be float32, got %s" % pc.dtype)
+    if pc.dim() != 3 or neighbor_idx.dim() != 3 or pc.shape[0] != neighbor_idx.shape[0]:
+        raise ValueError("gather_neighbour expects pc [B,N,d] and idx [B,N,K], got %s, %s"
+                         % (tuple(pc.shape), tuple(neighbor_idx.shape)))
+    return _GatherNeighbour.apply(pc, neighbor_idx)
+
+
+def relative_pos_encoding(xyz, neigh_idx):
+    """10-channel relative position encoding; mirrors
+    ``Building_block.relative_pos_encoding`` (models/RandLA/RandLANet.py:216-223).
+    Forward only (its inputs are coordinates and indices, neither requires grad in FFB6D).
+
+    :param xyz: [B, N, 3]; :param neigh_idx: [B, N, K]; :return: [B, N, K, 10]
+    """
+    _need_cuda(xyz, "xyz")
+    _need_cuda(neigh_idx, "neigh_idx")
+    xyz = xyz.contiguous().float()
+    idx_c, i64 = _idx_arg(neigh_idx, "neigh_idx")
+    if xyz.dim() != 3 or xyz.shape[2] != 3 or idx_c.dim() != 3 or idx_c.shape[:2] != xyz.shape[:2]:
+        raise ValueError("relative_pos_encoding expects xyz [B,N,3] and idx [B,N,K]")
+    B, N, _ = xyz.shape
+    K = idx_c.shape[2]
+    out = torch.empty((B, N, K, 10), dtype=torch.float32, device=xyz.device)
+    with torch.cuda.device(xyz.device):
+        check(lib.ffb6d_relative_pos_encoding_fwd(xyz.data_ptr(), idx_c.data_ptr(), i64, B, N, K,
+                                                  out.data_ptr(), _stream(xyz.device)))
+    return out
+
+
+# --------------------------------------------------------------------------- grid subsampling
+def grid_sub_sampling(points, features=None, labels=None, grid_size=0.1, verbose=0):
+    """Voxel-grid barycentre subsampling; mirrors ``DataProcessing.grid_sub_sampling``
+    (models/RandLA/helper_tool.py:199-219) and the wrapper's argument checks
+    (GS/cpp_subsampling/wrapper.cpp:96-190).
+
+    :param points: (N, 3) float32 points
+    :param features: optional (N, d) float32 features
+    :param labels: optional (N,) or (N, ld) int32 labels
+    :param grid_size: voxel size
+    :return: sub-sampled points, then features and/or labels if given (numpy arrays).
+      Rows are ordered by ascending voxel key (the reference's row order is that of a
+      hash map and carries no meaning).
+    """
+    pts = np.ascontiguousarray(points, dtype=np.float32)
+    if pts.ndim != 2 or pts.shape[1] != 3:
+        raise RuntimeError("Wrong dimensions : points.shape is not (N, 3)")      # wrapper.cpp:133-141
+    N = pts.shape[0]
+    if N < 1:
+        raise RuntimeError("Error")                                              # wrapper.cpp:225-229
+    feats = None
+    fdim = 0
+    if features is not None:
+        feats = np.ascontiguousarray(features, dtype=np.float32)
+        if feats.ndim != 2 or feats.shape[0] != N:
+            raise RuntimeError("Wrong dimensions : features.shape is not (N, d)")  # :143-159
+        fdim = feats.shape[1]
+    cls = None
+    ldim = 0
+    if labels is not None:
+        cls = np.ascontiguousarray(labels, dtype=np.int32)
+        if cls.ndim > 2 or cls.shape[0] != N:
+            raise RuntimeError("Wrong dimensions : classes.shape is not (N,) or (N, d)")  # :161-177
+        ldim = 1 if cls.ndim == 1 else cls.shape[1]
+    sub_p = np.empty((N, 3), np.float32)
+    sub_f = np.empty((N, max(fdim, 1)), np.float32)
+    sub_c = np.empty((N, max(ldim, 1)), np.int32)
+    M = C.c_size_t(0)
+    check(lib.ffb6d_grid_subsample_host(
+        pts.ctypes.data, N, feats.ctypes.data if feats is not None else None, fdim,
+        cls.ctypes.data if cls is not None else None, ldim, float(grid_size),
+        sub_p.ctypes.data, sub_f.ctypes.data, sub_c.ctypes.data, C.byref(M)))
+    m = M.value
+    out = [sub_p[:m].copy()]
+    if feats is not None:
+        out.append(sub_f[:m, :fdim].copy())
+    if cls is not None:
+        out.append(sub_c[:m, :ldim].copy())      # wrapper.cpp:240-243: classes come back [M, ld]
+    return out[0] if len(out) == 1 else tuple(out)

@@ -1,0 +1,105 @@
+"""One pass of the fusion hot path over a batch of frames (the unit bench.py times).
+
+A *pass* is what BASELINE.md §3 defines: the 22 KNN index builds of the dataset schedule
+(datasets/ycb/ycb_dataset.py:269-309) followed by the 11 ``random_sample``, 11
+``nearest_interpolation`` and 1 ``choose`` gathers of ``FFB6D.forward``
+(models/ffb6d.py:240-312), each gather consuming the index tensor the reference feeds it and
+a feature tensor of the width the reference has at that point.  The network layers between
+the gathers (cuDNN convs, 1x1 fusion MLPs) are not part of the pass, so the gather inputs are
+synthetic N(0,1) features resident in HBM.
+"""
+import torch
+
+from . import ops
+from . import schedule as S
+
+
+class FusionPass:
+    """Holds the device-resident feature tensors of one batch and runs passes over it.
+
+    :param batch: frames per pass (B)
+    :param n_points: sampled cloud size N0 (12288 in the reference, common.py:61)
+    :param layout: ``"nchw"`` -- features are contiguous [B,C,S,1] like the reference's;
+      ``"channels_last"`` -- same logical tensors in torch channels_last memory format.
+    """
+
+    def __init__(self, batch, n_points=12288, h=480, w=640, k=S.K_NEIGH, device="cuda",
+                 layout="nchw", seed=0, index_dtype=torch.int32):
+        self.B, self.n_points, self.h, self.w, self.k = batch, n_points, h, w, k
+        self.device = torch.device(device)
+        self.layout = layout
+        self.index_dtype = index_dtype
+        self.gathers = S.gather_schedule(n_points, h, w)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.features = []
+        for op, key, C, Sz, Q, K in self.gathers:
+            f = torch.randn((batch, C, Sz, 1), generator=g, device=self.device, dtype=torch.float32)
+            if layout == "channels_last":
+                f = f.contiguous(memory_format=torch.channels_last)
+            elif layout != "nchw":
+                raise ValueError("layout must be 'nchw' or 'channels_last'")
+            self.features.append(f)
+        kb, gb = S.frame_alg_bytes(n_points, h, w, k)
+        self.alg_bytes_per_frame = kb + gb
+        self.knn_alg_bytes_per_frame = kb
+        self.gather_alg_bytes_per_frame = gb
+
+    # -- the two halves of a pass ------------------------------------------------------
+    def build_indices(self, cld, dpt_xyz, choose, timer=None):
+        inputs = S.build_ffb6d_indices(cld, dpt_xyz, k=self.k, index_dtype=self.index_dtype,
+                                       timer=timer)
+        inputs["choose"] = choose
+        return inputs
+
+    def run_gathers(self, inputs, timer=None):
+        outs = []
+        for (op, key, C, Sz, Q, K), feat in zip(self.gathers, self.features):
+            idx = inputs[key]
+            if timer is not None:
+                timer.start("gather:%s" % key, S.gather_alg_bytes(C, Sz, Q, idx.shape[-1] if op != "choose" else 1) * self.B)
+            if op == "random_sample":
+                o = ops.random_sample(feat, idx)
+            elif op == "nearest_interpolation":
+                o = ops.nearest_interpolation(feat, idx)
+            else:
+                o = ops.choose_gather(feat.reshape(self.B, C, self.h, self.w) if self.layout == "nchw"
+                                      else feat.squeeze(3), idx)
+            if timer is not None:
+                timer.stop()
+            outs.append(o)
+        return outs
+
+    def __call__(self, cld, dpt_xyz, choose, timer=None):
+        """cld [B,N0,3] f32, dpt_xyz [B,H,W,3] f32, choose [B,1,N0] int -> (inputs dict, outputs)."""
+        inputs = self.build_indices(cld, dpt_xyz, choose, timer)
+        return inputs, self.run_gathers(inputs, timer)
+
+
+class OpTimer:
+    """CUDA-event pair per op on the current stream; durations are read after a synchronize."""
+
+    def __init__(self):
+        self.records = []          # (name, alg_bytes, start_event, stop_event)
+        self._cur = None
+
+    def start(self, name, alg_bytes):
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        self._cur = (name, alg_bytes, e0, e1)
+
+    def stop(self):
+        name, b, e0, e1 = self._cur
+        e1.record()
+        self.records.append((name, b, e0, e1))
+        self._cur = None
+
+    def summary(self):
+        """{name: {"ms": total, "bytes": total alg bytes, "launches": n}} (call after synchronize)."""
+        out = {}
+        for name, b, e0, e1 in self.records:
+            d = out.setdefault(name, {"ms": 0.0, "bytes": 0, "n": 0})
+            d["ms"] += e0.elapsed_time(e1)
+            d["bytes"] += b
+            d["n"] += 1
+        return out

@@ -1,0 +1,158 @@
+"""The per-frame KNN / gather schedule of FFB6D, and its one-call GPU index build.
+
+The reference builds 22 neighbour-index arrays per frame on the CPU inside the
+dataset (datasets/ycb/ycb_dataset.py:269-309 == datasets/linemod/linemod_dataset.py:313-353)
+and consumes them in ``FFB6D.forward`` through 22 gathers plus the ``choose``
+gather (models/ffb6d.py:231-312).  This module states both schedules as data and
+runs the index build on the GPU for a whole batch: xyz goes in, the same dict
+keys with the same shapes and dtypes (int32) come out, already on the device.
+"""
+import torch
+
+from .ops import knn_search
+
+# reference literals (ycb_dataset.py:269-271, 298)
+RGB_DS_SR = (4, 8, 8, 8)
+RGB_UP_SR = (4, 2, 2)
+PCLD_SUB_S_R = (4, 4, 4, 4)
+N_DS_LAYERS = 4
+N_UP_LAYERS = 3
+K_NEIGH = 16
+
+# feature widths seen by the gathers (models/ffb6d.py:49-50, 89-95; common.py:26)
+DS_RGB_OC = (64, 128, 512, 1024)
+DS_RNDLA_OC = (64, 128, 256, 512)
+UP_RGB_OC = (256, 64, 64)
+UP_RNDLA_OC = (256, 128, 64, 64)
+
+
+def knn_schedule(n_points=12288, h=480, w=640, k=K_NEIGH):
+    """The 22 KNN calls of one frame as ``(key, support, query, K)`` where support /
+    query name a point set: ``("cld", level)`` = first ``n_points / 4**level`` cloud
+    points, ``("img", sr)`` = the stride-``sr`` image pyramid level (``h//sr * w//sr``
+    points).  Order = the reference's call order."""
+    calls = []
+    for i in range(N_DS_LAYERS):
+        sr = RGB_DS_SR[i]
+        calls.append(("cld_nei_idx%d" % i, ("cld", i), ("cld", i), k))
+        calls.append(("cld_interp_idx%d" % i, ("cld", i + 1), ("cld", i), 1))
+        calls.append(("r2p_ds_nei_idx%d" % i, ("img", sr), ("cld", i + 1), k))
+        calls.append(("p2r_ds_nei_idx%d" % i, ("cld", i + 1), ("img", sr), 1))
+    for i in range(N_UP_LAYERS):
+        sr = RGB_UP_SR[i]
+        lvl = N_DS_LAYERS - i - 1
+        calls.append(("r2p_up_nei_idx%d" % i, ("img", sr), ("cld", lvl), k))
+        calls.append(("p2r_up_nei_idx%d" % i, ("cld", lvl), ("img", sr), 1))
+    return calls
+
+
+def set_size(name, n_points=12288, h=480, w=640):
+    kind, a = name
+    if kind == "cld":
+        n = n_points
+        for i in range(a):
+            n //= PCLD_SUB_S_R[min(i, len(PCLD_SUB_S_R) - 1)]
+        return n
+    return (h // a) * (w // a)
+
+
+def gather_schedule(n_points=12288, h=480, w=640):
+    """The 23 gathers of ``FFB6D.forward`` as ``(op, index_key, C, S, Q, K)`` in call
+    order (models/ffb6d.py:240-312).  ``op`` is ``"random_sample"``,
+    ``"nearest_interpolation"`` or ``"choose"``."""
+    N = [set_size(("cld", i), n_points) for i in range(5)]
+    HW = {sr: set_size(("img", sr), n_points, h, w) for sr in (1, 2, 4, 8)}
+    k = K_NEIGH
+    g = []
+    for i in range(N_DS_LAYERS):
+        sr = RGB_DS_SR[i]
+        g.append(("random_sample", "cld_sub_idx%d" % i, DS_RNDLA_OC[i], N[i], N[i + 1], k))
+        g.append(("nearest_interpolation", "p2r_ds_nei_idx%d" % i, DS_RGB_OC[i], N[i + 1], HW[sr], 1))
+        g.append(("random_sample", "r2p_ds_nei_idx%d" % i, DS_RGB_OC[i], HW[sr], N[i + 1], k))
+    up_in = (DS_RNDLA_OC[3], UP_RNDLA_OC[0], UP_RNDLA_OC[1])  # width entering each interp
+    for i in range(N_UP_LAYERS):
+        sr = RGB_UP_SR[i]
+        lvl = N_DS_LAYERS - i - 1
+        g.append(("nearest_interpolation", "cld_interp_idx%d" % lvl, up_in[i], N[lvl + 1], N[lvl], 1))
+        g.append(("nearest_interpolation", "p2r_up_nei_idx%d" % i, UP_RGB_OC[i], N[lvl], HW[sr], 1))
+        g.append(("random_sample", "r2p_up_nei_idx%d" % i, UP_RGB_OC[i], HW[sr], N[lvl], k))
+    g.append(("nearest_interpolation", "cld_interp_idx0", UP_RNDLA_OC[2], N[1], N[0], 1))
+    g.append(("choose", "choose", UP_RGB_OC[2], HW[1], N[0], 1))
+    return g
+
+
+def knn_alg_bytes(S, Q, K):
+    """Algorithmic HBM bytes of one KNN call: xyz in once, int32 idx out."""
+    return 12 * S + 12 * Q + 4 * Q * K
+
+
+def gather_alg_bytes(C, S, Q, K):
+    """Algorithmic HBM bytes of one gather: touched rows once, int32 idx,
+    output once."""
+    return 4 * C * min(S, Q * K) + 4 * Q * K + 4 * C * Q
+
+
+def frame_alg_bytes(n_points=12288, h=480, w=640, k=K_NEIGH):
+    """(knn_bytes, gather_bytes) per frame; 8 239 296 + 160 186 368 at the defaults."""
+    kb = sum(knn_alg_bytes(set_size(s, n_points, h, w), set_size(q, n_points, h, w), kk)
+             for _, s, q, kk in knn_schedule(n_points, h, w, k))
+    gb = 0
+    for op, _, Cc, S, Q, K in gather_schedule(n_points, h, w):
+        gb += gather_alg_bytes(Cc, S, Q, k if K == K_NEIGH else K)
+    return kb, gb
+
+
+def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
+    """``dpt_xyz [B,H,W,3]`` -> ``{sr: [B, (H//sr)*(W//sr), 3]}`` for sr in ``levels``: the
+    stride-``sr`` sub-grids of the organised cloud (ycb_dataset.py:253-267)."""
+    B, H, W, _ = dpt_xyz.shape
+    pyr = {}
+    for sr in levels:
+        nh, nw = H // sr, W // sr
+        pyr[sr] = dpt_xyz[:, :nh * sr:sr, :nw * sr:sr, :].reshape(B, nh * nw, 3).contiguous()
+    return pyr
+
+
+def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=None):
+    """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
+
+    :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
+    :param dpt_xyz: ``[B, H, W, 3]`` float32 CUDA, the organised cloud (zero rows at holes)
+    :param timer: optional object with ``start(name, alg_bytes)`` / ``stop()`` called around
+      every KNN call (bench.py's per-op CUDA-event timer)
+    :return: dict with the reference's keys (ycb_dataset.py:283-309), each with a leading
+      batch dimension: ``cld_xyz{i}`` f32 ``[B,Ni,3]``; ``cld_nei_idx{i}`` ``[B,Ni,k]``;
+      ``cld_sub_idx{i}`` ``[B,Ni/4,k]`` (the first Ni/4 rows of ``cld_nei_idx{i}``, :279);
+      ``cld_interp_idx{i}`` ``[B,Ni,1]``; ``r2p_ds_nei_idx{i}`` ``[B,Ni/4,k]``;
+      ``p2r_ds_nei_idx{i}`` ``[B,HW,1]``; ``r2p_up_nei_idx{i}``, ``p2r_up_nei_idx{i}``.
+      Index tensors are ``index_dtype`` (int32 like the datasets; pass torch.int64 to skip
+      the cast ``model_fn`` does, train_ycb.py:224-232).
+
+    "Random sampling" is the reference's: the cloud was shuffled once, every level keeps the
+    first quarter of the previous one (ycb_dataset.py:233-235, 278).
+    """
+    if cld.dim() != 3 or dpt_xyz.dim() != 4 or cld.shape[0] != dpt_xyz.shape[0]:
+        raise ValueError("expected cld [B,N,3] and dpt_xyz [B,H,W,3]")
+    cld = cld.contiguous().float()
+    B, n0, _ = cld.shape
+    H, W = dpt_xyz.shape[1], dpt_xyz.shape[2]
+    used = sorted(set(RGB_DS_SR) | set(RGB_UP_SR))          # sr=1 is never searched
+    sets = {("img", sr): p for sr, p in image_pyramid(dpt_xyz.float(), used).items()}
+    n = n0
+    for i in range(N_DS_LAYERS + 1):
+        sets[("cld", i)] = cld if i == 0 else cld[:, :n, :].contiguous()
+        if i < N_DS_LAYERS:
+            n //= PCLD_SUB_S_R[i]
+    inputs = {}
+    for key, s, q, kk in knn_schedule(n0, H, W, k):
+        sup, qry = sets[s], sets[q]
+        if timer is not None:
+            timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
+        inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype)
+        if timer is not None:
+            timer.stop()
+    for i in range(N_DS_LAYERS):
+        inputs["cld_xyz%d" % i] = sets[("cld", i)]
+        n_sub = sets[("cld", i + 1)].shape[1]
+        inputs["cld_sub_idx%d" % i] = inputs["cld_nei_idx%d" % i][:, :n_sub, :].contiguous()
+    return inputs

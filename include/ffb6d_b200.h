@@ -1,0 +1,175 @@
+/*
+ * ffb6d_b200.h -- C ABI of libffb6d_b200.so: the B200 (sm_100a) implementation of
+ * FFB6D's bidirectional-fusion hot path (KNN index build, gather + max-pool /
+ * nearest-feature gather, RandLA set-abstraction ops).
+ *
+ * Every entry point is extern "C", takes plain pointers and sizes, returns
+ * FFB6D_OK (0) or a negative error code, and never throws.  ffb6d_last_error()
+ * returns a thread-local, human readable message for the last failure.
+ *
+ * "Reference" citations below are relative to /root/reference/ffb6d/ of
+ * ethnhe/FFB6D @ e90baf73.  NN/ = models/RandLA/utils/nearest_neighbors/,
+ * GS/ = models/RandLA/utils/cpp_wrappers/.
+ *
+ * Pointer conventions
+ *   *_host entry points take HOST pointers and have the reference's own C++
+ *   signatures (NN/knn_.h:2-26): they are what the reference's Cython shim
+ *   (NN/knn.pyx:8-31) would bind instead of cpp_knn*.  They copy in, run the
+ *   CUDA kernels on the current device's default stream, copy out and
+ *   synchronise before returning -- the caller-visible behaviour of the
+ *   reference (blocking, caller-allocated output).
+ *   All other entry points take DEVICE pointers plus a cudaStream_t passed as
+ *   an opaque void* (NULL = default stream), are asynchronous, and never
+ *   allocate: temporary storage is caller-provided (see *_workspace_bytes).
+ *
+ * Index dtype: idx_is_i64 != 0 means int64 ("long", what NN/knn.pyx:93 allocates
+ * and what torch.gather consumes), 0 means int32 (what the datasets store,
+ * datasets/ycb/ycb_dataset.py:283-309).
+ *
+ * Feature layouts for the gather ops (the reference tensors are NCHW
+ * [B,C,S,1], models/ffb6d.py:159-194):
+ *   FFB6D_LAYOUT_NCS  feat[b][c][s]  (contiguous NCHW; point axis fastest)
+ *   FFB6D_LAYOUT_NSC  feat[b][s][c]  (torch channels_last view of the same
+ *                                     NCHW tensor; channel axis fastest)
+ * The output uses the layout of the input.
+ */
+#ifndef FFB6D_B200_H_
+#define FFB6D_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FFB6D_OK              0
+#define FFB6D_ERR_INVALID    -1   /* bad argument (shape, K, null pointer, layout) */
+#define FFB6D_ERR_CUDA       -2   /* a CUDA runtime call or kernel launch failed  */
+#define FFB6D_ERR_WORKSPACE  -3   /* workspace missing or too small               */
+#define FFB6D_ERR_NO_DEVICE  -4   /* no CUDA device visible                       */
+
+#define FFB6D_LAYOUT_NCS 0
+#define FFB6D_LAYOUT_NSC 1
+
+#define FFB6D_MAX_K 64            /* largest supported neighbour count */
+
+typedef void *ffb6d_stream_t;     /* cudaStream_t */
+
+/* ---- library ------------------------------------------------------------ */
+int ffb6d_version(void);                 /* ABI version, bumped on signature change */
+const char *ffb6d_last_error(void);      /* thread-local message of the last failure */
+int ffb6d_device_count(void);            /* number of CUDA devices, 0 if none / no driver */
+/* number of kernels this library has launched in this process (all threads).
+ * bench.py reports it as gpu_launches. */
+uint64_t ffb6d_launch_count(void);
+
+/* ---- KNN index build ---------------------------------------------------- */
+/*
+ * Exact K nearest neighbours of every query among the support points of the
+ * same batch item, ascending squared distance, fp32 arithmetic identical to
+ * nanoflann's L2_Adaptor for dim 3 (NN/nanoflann.hpp:343-346, no FMA).
+ * Replaces cpp_knn_batch / cpp_knn_batch_omp (NN/knn_.cxx:72-135).
+ *   support [B,S,3] f32, query [B,Q,3] f32 -> idx_out [B,Q,K] int32|int64
+ * Ties (exactly equal fp32 distances) are ordered by ascending support index
+ * (the reference orders them by KD-tree traversal; see DESIGN.md "tie contract").
+ * K > S: slots >= S are written as 0, as the reference leaves them (NN/knn_.cxx:120-121).
+ * Workspace: ffb6d_knn_workspace_bytes(B,S,Q,K) bytes of device memory, 256-byte
+ * aligned; may be NULL when that function returns 0.
+ */
+size_t ffb6d_knn_workspace_bytes(int64_t B, int64_t S, int64_t Q, int K);
+int ffb6d_knn_batch(const float *support, const float *query,
+                    int64_t B, int64_t S, int64_t Q, int K,
+                    void *idx_out, int idx_is_i64,
+                    void *workspace, size_t workspace_bytes,
+                    ffb6d_stream_t stream);
+
+/* Same, selecting the algorithm explicitly (testing / benchmarking):
+ * algo 0 = automatic, 1 = tiled brute force, 2 = uniform-grid search. */
+int ffb6d_knn_batch_algo(const float *support, const float *query,
+                         int64_t B, int64_t S, int64_t Q, int K,
+                         void *idx_out, int idx_is_i64,
+                         void *workspace, size_t workspace_bytes,
+                         int algo, ffb6d_stream_t stream);
+
+/* HOST-pointer twins with the reference's exact signatures (NN/knn_.h:2-16);
+ * dim must be 3.  `long` is int64 on LP64, as in the reference. */
+int ffb6d_knn_batch_host(const float *batch_data, size_t batch_size, size_t npts, size_t dim,
+                         const float *queries, size_t nqueries, size_t K, long *batch_indices);
+int ffb6d_knn_host(const float *points, size_t npts, size_t dim,
+                   const float *queries, size_t nqueries, size_t K, long *indices);
+
+/* ---- gather + max-pool / nearest gather -------------------------------- */
+/*
+ * out[b,c,q] = max_k feat[b,c,idx[b,q,k]]                       (K >= 1)
+ * Replaces FFB6D.random_sample / Network.random_sample (models/ffb6d.py:159-177,
+ * models/RandLA/RandLANet.py:87-102) and, with K == 1, FFB6D.nearest_interpolation
+ * (models/ffb6d.py:179-194, RandLANet.py:104-117) and the final `choose` gather
+ * (models/ffb6d.py:309-312).  Pure selection: results are bitwise equal to the
+ * reference (NaN propagates like torch.max).
+ *   feat [B,C,S] f32 in `layout`, idx [B,Q,K] -> out [B,C,Q] f32 in `layout`.
+ * Indices must lie in [0,S); they are not checked (torch.gather would raise).
+ */
+int ffb6d_gather_max_fwd(const float *feat, const void *idx, int idx_is_i64,
+                         int64_t B, int64_t C, int64_t S, int64_t Q, int K,
+                         int layout, float *out, ffb6d_stream_t stream);
+/*
+ * Backward of the above as autograd defines it for gather + max: grad_feat is
+ * zero-filled, then grad_out[b,c,q] is added at the arg-max neighbour (the first
+ * maximal k).  fp32 atomic adds: summation order is not deterministic, exactly
+ * as the reference's torch.gather backward on CUDA.
+ */
+int ffb6d_gather_max_bwd(const float *feat, const void *idx, int idx_is_i64,
+                         const float *grad_out,
+                         int64_t B, int64_t C, int64_t S, int64_t Q, int K,
+                         int layout, float *grad_feat, ffb6d_stream_t stream);
+
+/*
+ * out[b,n,k,:] = pc[b,idx[b,n,k],:]        channels-last neighbour gather
+ * Replaces Building_block.gather_neighbour (models/RandLA/RandLANet.py:225-234).
+ *   pc [B,S,D] f32, idx [B,N,K] -> out [B,N,K,D] f32
+ */
+int ffb6d_gather_neighbour_fwd(const float *pc, const void *idx, int idx_is_i64,
+                               int64_t B, int64_t S, int64_t D, int64_t N, int K,
+                               float *out, ffb6d_stream_t stream);
+int ffb6d_gather_neighbour_bwd(const float *grad_out, const void *idx, int idx_is_i64,
+                               int64_t B, int64_t S, int64_t D, int64_t N, int K,
+                               float *grad_pc, ffb6d_stream_t stream);
+
+/*
+ * Relative position encoding of RandLA's local spatial encoding
+ * (models/RandLA/RandLANet.py:216-223):
+ *   out[b,n,k,:] = [ ||xyz_n - xyz_j||, xyz_n - xyz_j, xyz_n, xyz_j ],  j = idx[b,n,k]
+ *   xyz [B,N,3] f32, idx [B,N,K] -> out [B,N,K,10] f32
+ * The norm is sqrt((dx*dx + dy*dy) + dz*dz) with round-to-nearest fp32 ops, the
+ * order torch.sum uses for a length-3 reduction.
+ */
+int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_is_i64,
+                                    int64_t B, int64_t N, int K,
+                                    float *out, ffb6d_stream_t stream);
+
+/* ---- grid subsampling --------------------------------------------------- */
+/*
+ * Voxel-grid barycentre subsampling, replaces grid_subsampling()
+ * (GS/cpp_subsampling/grid_subsampling/grid_subsampling.cpp:5-106) behind
+ * DataProcessing.grid_sub_sampling (models/RandLA/helper_tool.py:199-219).
+ * HOST pointers (the reference op is numpy-in / numpy-out).
+ *   points [N,3] f32, features [N,fdim] f32 or NULL, classes [N,ldim] i32 or NULL
+ *   -> sub_points [M,3], sub_features [M,fdim], sub_classes [M,ldim]; outputs must
+ *      have room for N rows; *M_out receives M.
+ * Rows are emitted by ascending voxel key (the reference's order is that of a
+ * libstdc++ unordered_map and is unspecified).  Per-voxel sums are accumulated in
+ * input order, so barycentres and mean features are bitwise equal to the
+ * reference; among labels tied for the maximal count the smallest is chosen.
+ */
+int ffb6d_grid_subsample_host(const float *points, size_t N,
+                              const float *features, size_t fdim,
+                              const int *classes, size_t ldim,
+                              float sampleDl,
+                              float *sub_points, float *sub_features, int *sub_classes,
+                              size_t *M_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FFB6D_B200_H_ */

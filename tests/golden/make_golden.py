@@ -1,0 +1,179 @@
+#!/usr/bin/env python
+"""Generate tests/golden/*.npz|json by running THE REFERENCE ITSELF in this container.
+
+Sources of truth (nothing here comes from our own oracle or CUDA code):
+  * KNN          oracle/_ref/libknn_ref.so  = unmodified NN/knn_.cxx + nanoflann.hpp
+                 (``make -C oracle ref``), called like nearest_neighbors.knn_batch.
+  * gathers      FFB6D.random_sample / nearest_interpolation (models/ffb6d.py:159-194) and
+                 Building_block.gather_neighbour / relative_pos_encoding
+                 (models/RandLA/RandLANet.py:216-234), executed from the reference's own
+                 source text (oracle/ref_loader.torch_functions), torch CPU, incl. autograd.
+  * grid         oracle/_ref/libgrid_ref.so = unmodified grid_subsampling.cpp + cloud.cpp.
+
+Run:  python tests/golden/make_golden.py      (needs /root/reference; rewrites the fixtures)
+The reference has no golden vectors of its own; these are the pin.
+"""
+import hashlib
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+from oracle import ref_loader as R                                   # noqa: E402
+from ffb6d_b200.synthetic import make_frame, image_pyramid_np       # noqa: E402
+from ffb6d_b200.schedule import knn_schedule                        # noqa: E402
+
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+
+def sha(a):
+    return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
+
+
+def point_sets(frame, n_points):
+    sets = {("cld", i): frame["cld"][: n_points // 4 ** i] for i in range(5)}
+    for sr, p in image_pyramid_np(frame["dpt_xyz"]).items():
+        sets[("img", sr)] = p
+    return sets
+
+
+def knn_cases():
+    """Small KNN problems with full inputs and reference outputs."""
+    cases = {}
+    fr = make_frame(3, n_points=3072)
+    ps = point_sets(fr, 3072)
+    # (name, support, query, K)
+    probs = [
+        ("self_768_k16", ps[("cld", 1)], ps[("cld", 1)], 16),
+        ("interp_192_768_k1", ps[("cld", 2)], ps[("cld", 1)], 1),
+        ("r2p_4800_192_k16", ps[("img", 8)], ps[("cld", 2)], 16),
+        ("p2r_192_4800_k1", ps[("cld", 2)], ps[("img", 8)], 1),
+        ("self_48_k16", ps[("cld", 3)], ps[("cld", 3)], 16),
+    ]
+    rs = np.random.RandomState(11)
+    u = rs.rand(1000, 3).astype(np.float32)
+    uq = rs.rand(500, 3).astype(np.float32)
+    probs += [("uniform_1000_500_k%d" % k, u, uq, k) for k in (1, 8, 32)]
+    probs.append(("k_gt_s_10_k16", u[:10], uq[:20], 16))           # trailing slots stay 0
+    # exact-distance ties: duplicated support points (the datasets' 'wrap' padding)
+    base = rs.rand(192, 3).astype(np.float32)
+    dup = np.concatenate([base, base[:64]])[rs.permutation(256)]
+    probs.append(("ties_256_k8", dup, dup, 8))
+    for name, s, q, k in probs:
+        idx = R.knn_batch(s[None], q[None], k, omp=False)[0]
+        idx_omp = R.knn_batch(s[None], q[None], k, omp=True)[0]
+        assert np.array_equal(idx, idx_omp), name
+        cases[name + "/support"] = s
+        cases[name + "/query"] = q
+        cases[name + "/k"] = np.int32(k)
+        cases[name + "/idx"] = idx.astype(np.int32)
+    # a batched call (B=3) to pin the batch stride handling
+    frames = [make_frame(s, n_points=768) for s in (5, 6, 7)]
+    sup = np.stack([f["cld"] for f in frames])
+    cases["batch3_768_k16/support"] = sup
+    cases["batch3_768_k16/query"] = sup
+    cases["batch3_768_k16/k"] = np.int32(16)
+    cases["batch3_768_k16/idx"] = R.knn_batch(sup, sup, 16, omp=True).astype(np.int32)
+    return cases
+
+
+def schedule_digest(seed, n_points):
+    """sha256 of each of the 22 reference index arrays of one full synthetic frame."""
+    fr = make_frame(seed, n_points=n_points)
+    ps = point_sets(fr, n_points)
+    dig = {}
+    for key, s, q, k in knn_schedule(n_points):
+        idx = R.knn_search(ps[s][None], ps[q][None], k, omp=False)[0]      # int32 like the dataset
+        dig[key] = {"sha256": sha(idx), "shape": list(idx.shape), "S": int(len(ps[s])), "K": k}
+    return dig
+
+
+def gather_cases():
+    f = R.torch_functions()
+    g = torch.Generator().manual_seed(1234)
+    cases = {}
+
+    def rnd(*shape):
+        return torch.randn(*shape, generator=g)
+
+    def rint(hi, *shape):
+        return torch.randint(0, hi, shape, generator=g)
+
+    for name, (B, Cc, S, Q, K) in {"rs_small": (2, 8, 100, 30, 16), "rs_k8": (1, 5, 77, 41, 8),
+                                   "rs_wide": (2, 130, 48, 12, 16)}.items():
+        feat = rnd(B, Cc, S, 1).requires_grad_(True)
+        idx = rint(S, B, Q, K)
+        out = f["random_sample"](feat, idx)
+        go = rnd(*out.shape)
+        out.backward(go)
+        cases.update({name + "/feat": feat.detach().numpy(), name + "/idx": idx.numpy(),
+                      name + "/out": out.detach().numpy(), name + "/gout": go.numpy(),
+                      name + "/gfeat": feat.grad.numpy()})
+    for name, (B, Cc, S, Q) in {"ni_small": (2, 8, 48, 200), "ni_wide": (1, 64, 30, 100)}.items():
+        feat = rnd(B, Cc, S, 1).requires_grad_(True)
+        idx = rint(S, B, Q, 1)
+        out = f["nearest_interpolation"](feat, idx)
+        go = rnd(*out.shape)
+        out.backward(go)
+        cases.update({name + "/feat": feat.detach().numpy(), name + "/idx": idx.numpy(),
+                      name + "/out": out.detach().numpy(), name + "/gout": go.numpy(),
+                      name + "/gfeat": feat.grad.numpy()})
+    for name, (B, N, D, K) in {"gn_xyz": (2, 100, 3, 16), "gn_feat": (2, 60, 16, 16),
+                               "gn_odd": (1, 33, 5, 7)}.items():
+        pc = rnd(B, N, D).requires_grad_(True)
+        idx = rint(N, B, N, K)
+        out = f["gather_neighbour"](pc, idx)
+        go = rnd(*out.shape)
+        out.backward(go)
+        cases.update({name + "/pc": pc.detach().numpy(), name + "/idx": idx.numpy(),
+                      name + "/out": out.detach().numpy(), name + "/gout": go.numpy(),
+                      name + "/gpc": pc.grad.numpy()})
+    xyz = rnd(2, 100, 3)
+    idx = rint(100, 2, 100, 16)
+    cases.update({"rpe/xyz": xyz.numpy(), "rpe/idx": idx.numpy(),
+                  "rpe/out": f["relative_pos_encoding"](xyz, idx).numpy()})
+    return cases
+
+
+def grid_cases():
+    cases = {}
+    rs = np.random.RandomState(21)
+    pts = (rs.rand(6000, 3) * np.array([2.0, 1.5, 0.7])).astype(np.float32) - 0.4
+    feats = rs.rand(6000, 4).astype(np.float32)
+    labels = rs.randint(0, 5, (6000,)).astype(np.int32)
+    for name, dl in (("g010", 0.10), ("g004", 0.04)):
+        p, fe, la = R.grid_subsampling(pts, feats, labels, dl)
+        order = np.lexsort((p[:, 2], p[:, 1], p[:, 0]))
+        cases.update({name + "/dl": np.float32(dl), name + "/sub_points": p[order],
+                      name + "/sub_features": fe[order], name + "/sub_labels": la[order]})
+    (p_only,) = R.grid_subsampling(pts, None, None, 0.1)
+    order = np.lexsort((p_only[:, 2], p_only[:, 1], p_only[:, 0]))
+    cases["g010/points_only"] = p_only[order]
+    cases["points"] = pts
+    cases["features"] = feats
+    cases["labels"] = labels
+    return cases
+
+
+def main():
+    if not R.reference_sources_present():
+        raise SystemExit("needs /root/reference")
+    R.build_ref()
+    np.savez_compressed(os.path.join(OUT, "knn_cases.npz"), **knn_cases())
+    np.savez_compressed(os.path.join(OUT, "gather_cases.npz"), **gather_cases())
+    np.savez_compressed(os.path.join(OUT, "grid_cases.npz"), **grid_cases())
+    dig = {"generator": "ffb6d_b200.synthetic.make_frame", "frames": {}}
+    for seed, n in ((0, 12288), (1, 12288), (2, 3072)):
+        dig["frames"]["seed%d_n%d" % (seed, n)] = {"seed": seed, "n_points": n,
+                                                    "keys": schedule_digest(seed, n)}
+    with open(os.path.join(OUT, "schedule_digest.json"), "w") as fh:
+        json.dump(dig, fh, indent=1, sort_keys=True)
+    print("golden fixtures written to", OUT)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,57 @@
+"""CPU, only where /root/reference exists (this container): the oracle against the
+reference's own code executed live on fresh random inputs."""
+import numpy as np
+import pytest
+
+from oracle import cpu_oracle as O
+from oracle import ref_loader as R
+
+pytestmark = pytest.mark.skipif(not (R.reference_sources_present() and R.knn_available()),
+                                reason="reference sources / oracle/_ref not present on this box")
+
+
+@pytest.mark.parametrize("seed,S,Q,K", [(0, 500, 300, 16), (1, 2000, 100, 1), (2, 64, 64, 32),
+                                        (3, 5, 9, 8), (4, 3000, 700, 4)])
+def test_knn_random(seed, S, Q, K):
+    rs = np.random.RandomState(seed)
+    sup = rs.randn(2, S, 3).astype(np.float32)
+    qry = rs.randn(2, Q, 3).astype(np.float32)
+    want = R.knn_batch(sup, qry, K, omp=True)
+    got = O.knn_batch(sup, qry, K)
+    ok, ndiff, _, msg = O.knn_matches(sup, qry, got, want)
+    assert ok and ndiff == 0, msg
+
+
+def test_knn_surface_frame():
+    from ffb6d_b200.synthetic import make_frame
+    fr = make_frame(9, n_points=3072)
+    cld = fr["cld"][None]
+    assert np.array_equal(O.knn_batch(cld, cld, 16), R.knn_batch(cld, cld, 16))
+
+
+def test_torch_ops_random():
+    import torch
+    f = R.torch_functions()
+    g = torch.Generator().manual_seed(7)
+    feat = torch.randn(3, 17, 211, 1, generator=g)
+    idx = torch.randint(0, 211, (3, 50, 16), generator=g)
+    assert np.array_equal(f["random_sample"](feat, idx).numpy(), O.random_sample(feat.numpy(), idx.numpy()))
+    idx1 = torch.randint(0, 211, (3, 400, 1), generator=g)
+    assert np.array_equal(f["nearest_interpolation"](feat, idx1).numpy(),
+                          O.nearest_interpolation(feat.numpy(), idx1.numpy()))
+    pc = torch.randn(2, 90, 6, generator=g)
+    nidx = torch.randint(0, 90, (2, 90, 16), generator=g)
+    assert np.array_equal(f["gather_neighbour"](pc, nidx).numpy(),
+                          O.gather_neighbour(pc.numpy(), nidx.numpy()))
+
+
+@pytest.mark.skipif(not R.grid_available(), reason="oracle/_ref/libgrid_ref.so missing")
+def test_grid_random():
+    rs = np.random.RandomState(5)
+    pts = (rs.randn(4000, 3) * 0.5).astype(np.float32)
+    feats = rs.rand(4000, 3).astype(np.float32)
+    rp, rf = R.grid_subsampling(pts, feats, None, 0.07)
+    op, of, _ = O.grid_sub_sampling(pts, feats, None, 0.07)
+    o1 = np.lexsort((rp[:, 2], rp[:, 1], rp[:, 0]))
+    o2 = np.lexsort((op[:, 2], op[:, 1], op[:, 0]))
+    assert np.array_equal(rp[o1], op[o2]) and np.array_equal(rf[o1], of[o2])
