@@ -236,6 +236,7 @@ def main():
     ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"])
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per CPU-arm sample (0 = #cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA graph replays")
     ap.add_argument("--per-op", action="store_true", help="also print the per-op table to stderr")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -278,42 +279,71 @@ def main():
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ
                            else os.environ["CUDA_VISIBLE_DEVICES"].split(",")[local_rank]) if rank == 0 else None
 
-    # ---- warm-up
+    # ---- warm-up (eager), then capture the pass into CUDA graphs: ~200 small launches with
+    # static shapes per step; replaying removes the Python/launch overhead from the GPU timeline
     for _ in range(args.warmup):
         p(cld_d, xyz_d, cho_d)
     torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    p(cld_d, xyz_d, cho_d)
+    launches_per_step = _lib.launch_count() - l0
+    use_graph = not args.no_graph
+    run_resident = None
+    if use_graph:
+        try:
+            run_resident = p.capture(cld_d, xyz_d, cho_d)
+        except Exception as e:                      # noqa: BLE001
+            sys.stderr.write("bench.py: CUDA graph capture failed (%s); timing eager launches\n" % e)
+            use_graph = False
+    if run_resident is None:
+        def run_resident():
+            return p(cld_d, xyz_d, cho_d)
+    for _ in range(2):
+        run_resident()
+    torch.cuda.synchronize()
 
-    # ---- timed region 1: inputs resident in HBM, per-op events on the launching stream
-    timer = OpTimer()
+    # ---- timed region 1: inputs resident in HBM
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
     torch.cuda.synchronize()
-    l0 = _lib.launch_count()
     e0.record()
     for _ in range(args.steps):
-        inputs, outs = p(cld_d, xyz_d, cho_d, timer)
+        run_resident()
     e1.record()
     torch.cuda.synchronize()
     barrier()
-    launches = _lib.launch_count() - l0
+    launches = launches_per_step * args.steps
     ms = e0.elapsed_time(e1)
 
-    # ---- timed region 2: end to end (H2D of the step's xyz inputs, pass, D2H of a result digest)
+    # ---- timed region 2: end to end (H2D of the step's xyz inputs from pinned memory, the
+    # pass, D2H of a result digest into pinned memory)
     digest_h = torch.empty((len(p.gathers) + 22) * 256, dtype=torch.float32).pin_memory()
 
-    def e2e_step():
-        c = cld_h.to(dev, non_blocking=True)
-        x = xyz_h.to(dev, non_blocking=True)
-        ch = cho_h.to(dev, non_blocking=True)
-        inp, out = p(c, x, ch)
+    def digest_fn(inp, out):
         parts = [o.reshape(-1)[:256] for o in out]
         parts += [inp[k].reshape(-1)[:256].float() for k in sorted(inp) if "idx" in k and "sub" not in k]
-        d = torch.cat(parts)
-        digest_h[: d.numel()].copy_(d, non_blocking=True)
-        return d.numel()
+        return torch.cat(parts)
 
+    ndig = (len(p.gathers) + 22) * 256
+    cld_s, xyz_s, cho_s = torch.empty_like(cld_d), torch.empty_like(xyz_d), torch.empty_like(cho_d)
+    run_e2e = None
+    if use_graph:
+        try:
+            run_e2e = p.capture(cld_s, xyz_s, cho_s, host_inputs=(cld_h, xyz_h, cho_h),
+                                digest=(digest_fn, digest_h))
+        except Exception as e:                      # noqa: BLE001
+            sys.stderr.write("bench.py: e2e graph capture failed (%s); eager\n" % e)
+    if run_e2e is None:
+        def run_e2e():
+            cld_s.copy_(cld_h, non_blocking=True)
+            xyz_s.copy_(xyz_h, non_blocking=True)
+            cho_s.copy_(cho_h, non_blocking=True)
+            res = p(cld_s, xyz_s, cho_s)
+            d = digest_fn(*res)
+            digest_h[: d.numel()].copy_(d, non_blocking=True)
+            return res
     for _ in range(2):
-        e2e_step()
+        run_e2e()
     torch.cuda.synchronize()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -321,12 +351,26 @@ def main():
     t0 = time.perf_counter()
     f0.record()
     for _ in range(args.steps):
-        ndig = e2e_step()
+        run_e2e()
     f1.record()
     torch.cuda.synchronize()
     e2e_wall_ms = (time.perf_counter() - t0) * 1e3
     barrier()
     e2e_ms = max(f0.elapsed_time(f1), e2e_wall_ms)
+
+    # ---- instrumented region: the same launches issued eagerly with a CUDA-event pair around
+    # every op, on the launching stream.  A spin kernel in front of each step keeps the GPU
+    # behind the CPU so the events bracket kernel time, not Python launch gaps.
+    timer = OpTimer()
+    i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    inst_ms = 0.0
+    for _ in range(args.steps):
+        torch.cuda._sleep(int(40e6))
+        i0.record()
+        p(cld_d, xyz_d, cho_d, timer)
+        i1.record()
+        torch.cuda.synchronize()
+        inst_ms += i0.elapsed_time(i1)
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- max over ranks
@@ -364,7 +408,7 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-        "share_of_step": dd["ms"] / tot_ms, "launches_per_step": dd["n"] // steps,
+        "share_of_step": dd["ms"] / tot_ms, "ops_per_step": dd["n"] // steps,
         "alg_bytes_per_launch": dd["bytes"] / dd["n"], "avg_launch_ms": dd["ms"] / dd["n"],
         "families": {k: {"share": v["ms"] / tot_ms, "ms_per_step": v["ms"] / steps,
                          "GBps": v["bytes"] / (v["ms"] / 1e3) / 1e9} for k, v in sorted(fam.items())},
@@ -406,7 +450,8 @@ def main():
                 "note": "H2D = cld + organised xyz + choose from pinned memory; D2H = 256-element digest of "
                         "each of the 45 results; gather features are device-resident activations as in the "
                         "reference (they are produced on the GPU by the network)"},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
+        "instrumented_ms_per_step": inst_ms / steps, "sum_of_ops_ms_per_step": tot_ms / steps,
         "roofline": roofline, "pass_roofline": pass_roofline,
         "cpu_baseline": cpu_baseline, "clocks": clocks,
     }

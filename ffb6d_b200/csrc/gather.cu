@@ -20,10 +20,17 @@
 //   contiguous row read (embedding-lookup pattern).
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace ffb6d {
 
 // torch.max semantics: NaN propagates; first maximal element wins the arg-max
-__device__ __forceinline__ float max_nan(float m, float v) { return (v > m || v != v) ? v : m; }
+__device__ __forceinline__ float max_nan(float m, float v)
+{
+    float r;   // FMNMX.NAN: NaN if either operand is NaN, like torch.max
+    asm("max.NaN.f32 %0, %1, %2;" : "=f"(r) : "f"(m), "f"(v));
+    return r;
+}
 
 template <typename IdxT, int KT>
 __device__ __forceinline__ void load_ids(const IdxT *__restrict__ ip, int K, int (&id)[KT > 0 ? KT : 1])
@@ -103,12 +110,61 @@ gather_max_ncs_staged_kernel(const float *__restrict__ feat, const IdxT *__restr
     }
 }
 
+// ------------------------------------------------------------------ NCS staged, K == 1, four queries per thread
+// nearest_interpolation / p2r gathers: small source rows, long query lists.  A thread takes four
+// consecutive queries (one 128-bit index load), reads the four values of each staged row from
+// shared memory and writes them with one 128-bit store: the output stream is the only HBM
+// traffic that matters here and it is written in 512-byte warp bursts.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather1_ncs_staged_v4_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                             float *__restrict__ out, int C, int S, int Q, int CC, int q_per_cta)
+{
+    extern __shared__ __align__(16) float rows[];  // [cc][S]
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * CC;
+    const int cc = min(CC, C - c0);
+    const float *src = feat + ((size_t)b * C + c0) * S;
+    const int n = cc * S;
+    if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
+        const float4 *s4 = reinterpret_cast<const float4 *>(src);
+        float4 *d4 = reinterpret_cast<float4 *>(rows);
+        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
+    } else {
+        for (int t = threadIdx.x; t < n; t += blockDim.x) rows[t] = __ldg(src + t);
+    }
+    __syncthreads();
+    const int q0 = blockIdx.x * q_per_cta;          // multiple of 4
+    const int q1 = min(Q, q0 + q_per_cta);          // Q is a multiple of 4
+    float *dst = out + ((size_t)b * C + c0) * Q;
+    const IdxT *ib = idx + (size_t)b * Q;
+    for (int q = q0 + threadIdx.x * 4; q < q1; q += blockDim.x * 4) {
+        int i0, i1, i2, i3;
+        if constexpr (sizeof(IdxT) == 4) {
+            const int4 v = __ldg(reinterpret_cast<const int4 *>(ib + q));
+            i0 = v.x; i1 = v.y; i2 = v.z; i3 = v.w;
+        } else {
+            const longlong2 u = __ldg(reinterpret_cast<const longlong2 *>(ib + q));
+            const longlong2 w = __ldg(reinterpret_cast<const longlong2 *>(ib + q) + 1);
+            i0 = (int)u.x; i1 = (int)u.y; i2 = (int)w.x; i3 = (int)w.y;
+        }
+#pragma unroll 4
+        for (int c = 0; c < cc; ++c) {
+            const float *r = rows + c * S;
+            const float4 v = make_float4(r[i0], r[i1], r[i2], r[i3]);
+            __stcs(reinterpret_cast<float4 *>(dst + (size_t)c * Q + q), v);   // streaming store
+        }
+    }
+}
+
 // ------------------------------------------------------------------ NCS direct
 template <typename IdxT, int KT>
 __global__ void __launch_bounds__(256)
 gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
                              float *__restrict__ out, int C, int S, int Q, int K, int CC)
 {
+    // rows too long for shared memory: neighbour values come through L1/L2.  All loads of a
+    // channel pair are issued before the first use so 2*K requests per thread are in flight.
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * CC;
     const int cc = min(CC, C - c0);
@@ -120,14 +176,30 @@ gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restr
     if constexpr (KT > 0) {
         int id[KT];
         load_ids<IdxT, KT>(ip, K, id);
-        for (int c = 0; c < cc; ++c) {
+        int c = 0;
+        for (; c + 1 < cc; c += 2) {
+            const float *r0 = src + (size_t)c * S;
+            const float *r1 = r0 + S;
+            float v0[KT], v1[KT];
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                v0[k] = __ldg(r0 + id[k]);
+                v1[k] = __ldg(r1 + id[k]);
+            }
+            float m0 = v0[0], m1 = v1[0];
+#pragma unroll
+            for (int k = 1; k < KT; ++k) {
+                m0 = max_nan(m0, v0[k]);
+                m1 = max_nan(m1, v1[k]);
+            }
+            dst[(size_t)c * Q + q] = m0;
+            dst[(size_t)(c + 1) * Q + q] = m1;
+        }
+        if (c < cc) {
             const float *r = src + (size_t)c * S;
-            float v[KT];
+            float m = __ldg(r + id[0]);
 #pragma unroll
-            for (int k = 0; k < KT; ++k) v[k] = __ldg(r + id[k]);
-            float m = v[0];
-#pragma unroll
-            for (int k = 1; k < KT; ++k) m = max_nan(m, v[k]);
+            for (int k = 1; k < KT; ++k) m = max_nan(m, __ldg(r + id[k]));
             dst[(size_t)c * Q + q] = m;
         }
     } else {
@@ -138,6 +210,27 @@ gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restr
             dst[(size_t)c * Q + q] = m;
         }
     }
+}
+
+// K == 1 with long rows (the `choose` gather): eight channels per thread, loads first
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+gather1_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                          float *__restrict__ out, int C, int S, int Q)
+{
+    const int b = blockIdx.z;
+    const int c0 = blockIdx.y * 8;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const int id = (int)__ldg(idx + (size_t)b * Q + q);
+    const float *src = feat + ((size_t)b * C + c0) * S + id;
+    float *dst = out + ((size_t)b * C + c0) * Q + q;
+    float v[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) v[c] = (c0 + c < C) ? __ldg(src + (size_t)c * S) : 0.f;
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (c0 + c < C) __stcs(dst + (size_t)c * Q, v[c]);
 }
 
 // ------------------------------------------------------------------ NSC (channels last)
@@ -157,27 +250,37 @@ gather_max_nsc_kernel(const float *__restrict__ feat, const IdxT *__restrict__ i
     // lanes fetch the indices once (K <= 64)
     int my0 = (lane < K) ? (int)__ldg(ip + lane) : 0;
     int my1 = (lane + 32 < K) ? (int)__ldg(ip + lane + 32) : 0;
+    // trip counts are warp-uniform: every lane takes part in the index shuffles
     if ((C & 3) == 0) {
-        for (int c = lane * 4; c < C; c += 128) {
-            float4 m = __ldg(reinterpret_cast<const float4 *>(base + (size_t)__shfl_sync(0xffffffffu, my0, 0) * C + c));
+        for (int c0 = 0; c0 < C; c0 += 128) {
+            const int c = c0 + lane * 4;
+            const bool on = c < C;
+            const int s0 = __shfl_sync(0xffffffffu, my0, 0);
+            float4 m = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (on) m = __ldg(reinterpret_cast<const float4 *>(base + (size_t)s0 * C + c));
             for (int k = 1; k < K; ++k) {
                 const int s = __shfl_sync(0xffffffffu, (k < 32) ? my0 : my1, k & 31);
-                const float4 v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)s * C + c));
-                m.x = max_nan(m.x, v.x);
-                m.y = max_nan(m.y, v.y);
-                m.z = max_nan(m.z, v.z);
-                m.w = max_nan(m.w, v.w);
+                if (on) {
+                    const float4 v = __ldg(reinterpret_cast<const float4 *>(base + (size_t)s * C + c));
+                    m.x = max_nan(m.x, v.x);
+                    m.y = max_nan(m.y, v.y);
+                    m.z = max_nan(m.z, v.z);
+                    m.w = max_nan(m.w, v.w);
+                }
             }
-            *reinterpret_cast<float4 *>(o + c) = m;
+            if (on) *reinterpret_cast<float4 *>(o + c) = m;
         }
     } else {
-        for (int c = lane; c < C; c += 32) {
-            float m = __ldg(base + (size_t)__shfl_sync(0xffffffffu, my0, 0) * C + c);
+        for (int c0 = 0; c0 < C; c0 += 32) {
+            const int c = c0 + lane;
+            const bool on = c < C;
+            const int s0 = __shfl_sync(0xffffffffu, my0, 0);
+            float m = on ? __ldg(base + (size_t)s0 * C + c) : 0.f;
             for (int k = 1; k < K; ++k) {
                 const int s = __shfl_sync(0xffffffffu, (k < 32) ? my0 : my1, k & 31);
-                m = max_nan(m, __ldg(base + (size_t)s * C + c));
+                if (on) m = max_nan(m, __ldg(base + (size_t)s * C + c));
             }
-            o[c] = m;
+            if (on) o[c] = m;
         }
     }
 }
@@ -318,27 +421,55 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
     const size_t row_bytes = (size_t)S * sizeof(float);
     // rows that fit shared memory twice over (two CTAs per SM hide the staging latency)
     const size_t budget = (size_t)smem_cap / 2;
+    const int64_t want = 4 * kNumSMs;   // CTAs to aim for
     if (row_bytes <= budget) {
         int CC = (int)(budget / row_bytes);
         if (CC > C) CC = (int)C;
-        // enough CTAs to fill the chip: split the channel range first, then the queries
-        const int64_t want = 2 * kNumSMs;
-        while (CC > 1 && B * ceil_div(C, CC) < want) CC = (CC + 1) / 2;
-        int64_t nq = 1;
+        // the K indices of a query are re-read once per channel chunk: keep chunks wide when K
+        // is large (index bytes ~ K/CC of the output bytes), narrow when K == 1
+        const int cc_cap = (KT == 1) ? 8 : 32;
+        if (CC > cc_cap) CC = cc_cap;
+        while (CC > 1 && B * ceil_div(C, CC) < want && (KT == 1 || CC > 4)) CC = (CC + 1) / 2;
         const int64_t ctas = B * ceil_div(C, CC);
-        if (ctas < want) nq = ceil_div(want, ctas);
+        int64_t nq = ctas < want ? ceil_div(want, ctas) : 1;
+        // every query chunk stages the rows again: keep a chunk at least 4 rows long
         int64_t q_per_cta = ceil_div(Q, nq);
-        if (q_per_cta < 256) q_per_cta = 256;
+        const int64_t q_min = std::max<int64_t>(1024, 4 * S);
+        if (q_per_cta < q_min) q_per_cta = q_min;
+        q_per_cta = ceil_div(q_per_cta, 1024) * 1024;
         nq = ceil_div(Q, q_per_cta);
         const size_t smem = (size_t)CC * row_bytes;
-        auto kern = gather_max_ncs_staged_kernel<IdxT, KT>;
-        if (smem > 48 * 1024)
-            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)smem));
         dim3 grid((unsigned)nq, (unsigned)ceil_div(C, CC), (unsigned)B);
+        if constexpr (KT == 1) {
+            const bool v4 = (Q % 4 == 0) && ((reinterpret_cast<uintptr_t>(idx) & 15) == 0) &&
+                            ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+            if (v4) {
+                auto kern = gather1_ncs_staged_v4_kernel<IdxT>;
+                static bool optin_done = false;
+                if (!optin_done) {
+                    FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                    max_smem_optin()));
+                    optin_done = true;
+                }
+                kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, CC, (int)q_per_cta);
+                FFB6D_LAUNCH_OK("gather1_ncs_staged_v4_kernel");
+                return FFB6D_OK;
+            }
+        }
+        auto kern = gather_max_ncs_staged_kernel<IdxT, KT>;
+        static bool optin_done = false;   // once per instantiation (not a stream op: keep it out of graphs)
+        if (!optin_done) {
+            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            max_smem_optin()));
+            optin_done = true;
+        }
         kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, CC,
                                       (int)q_per_cta);
         FFB6D_LAUNCH_OK("gather_max_ncs_staged_kernel");
+    } else if (KT == 1) {
+        dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, 8), (unsigned)B);
+        gather1_ncs_direct_kernel<IdxT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
+        FFB6D_LAUNCH_OK("gather1_ncs_direct_kernel");
     } else {
         const int CC = 8;
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, CC), (unsigned)B);

@@ -21,6 +21,14 @@ struct TopK {
         }
     }
     __device__ __forceinline__ float worst() const { return d[KCAP - 1]; }
+    // distance of the K-th entry (1 <= K <= KCAP) without dynamic register indexing
+    __device__ __forceinline__ float kth(int K) const
+    {
+        float v = d[KCAP - 1];
+#pragma unroll
+        for (int j = KCAP - 2; j >= 0; --j) v = (j >= K - 1) ? d[j] : v;
+        return v;
+    }
     __device__ __forceinline__ int worst_idx() const { return i[KCAP - 1]; }
 
     // Candidates arrive in ascending index order: a candidate goes behind every

@@ -1,13 +1,908 @@
-// knn_grid.cu -- uniform-grid exact KNN (placeholder until the grid search lands:
-// it declines every problem so the dispatcher uses the tiled scan).
+// knn_grid.cu -- exact KNN through a uniform grid over the support cloud (sm_100a).
+//
+// The reference answers every query with a KD-tree descent (NN/nanoflann.hpp:1350-1408).
+// On the GPU the same *result* -- the K support points with the smallest reference-arithmetic
+// fp32 distance, ordered by (distance, index) -- is produced by binning the support into a
+// uniform grid and scanning only the cells around each query:
+//
+//   A. prepare  : per batch item min/max of the support (chunked over CTAs; the last CTA to
+//                 finish reduces the partials), an ESTIMATE of the K-th neighbour distance from
+//                 32 sample points scanned against a strided subsample, and from it the cell
+//                 edge h and grid dims; the item's cell counters are zeroed
+//   B. count    : one atomic per point into its cell's counter (+ a per-4096-cell tile total)
+//   C. scan     : exclusive prefix sum of the counters (cell -> first slot), one CTA per tile
+//   D. scatter  : points (x,y,z,index) written cell-contiguous as float4
+//   E. search   : one thread per query scans the (2r+1)^3 block of cells around it, r = 1..RMAX
+//                 (each ring adds only its shell of cells), keeping a sorted top-K in registers; a row of cells along x is one contiguous
+//                 range of the sorted array, read four points at a time.  The search stops as
+//                 soon as the K-th distance is provably smaller than the distance to anything
+//                 outside the block.
+//   F. overflow : queries that cannot be certified within RMAX rings (far from the support: the
+//                 (0,0,0) hole pixels of the organised cloud, K > S, ...) are answered by a tiled
+//                 scan of the whole support.  Far queries that are equal to the first
+//                 far query of their batch item (all hole pixels are) are not searched again:
+//   G. dup copy : they receive a copy of that query's result row.
+//
+// Exactness: candidates are evaluated with the reference arithmetic (common.cuh ref_sqdist) and
+// ranked by the total order (distance, index), so the result does not depend on the order in
+// which cells or points are visited, nor on h or the estimate; the stop test is conservative
+// (see `slack`).  HBM traffic per call is ~ the algorithmic 12S + 12Q + 4QK plus the 16S sorted
+// copy and the cell table; everything else stays in L1/L2.
 #include "common.cuh"
 #include "knn_common.cuh"
+
+#include <algorithm>
+#include <math.h>
+#include <stdlib.h>
+
 namespace ffb6d {
-size_t knn_grid_workspace_bytes(int64_t, int64_t, int64_t, int) { return 0; }
-int knn_grid_launch(const float *, const float *, int64_t, int64_t, int64_t, int, void *, int, void *,
-                    size_t, cudaStream_t)
+
+constexpr int RMAX = 4;                 // widest block: 9x9x9 cells
+constexpr int PREP_THREADS = 1024;
+constexpr int MAX_CHUNKS = 64;          // partial bboxes per batch item
+constexpr int TILE_CELLS = 4096;        // cells per scan tile
+constexpr int N_SAMPLES = 32;           // one per warp of the prepare CTA
+
+struct __align__(16) GridParams {
+    float lo[3];
+    float h;        // cell edge
+    float inv_h;    // 0 when the grid is a single cell along every axis
+    float slack;    // absolute safety margin of the stop test
+    int n[3];       // cells per axis
+    int ncells;
+    int ovf_count;  // queries handed to the overflow pass (front of the ovf list)
+    int dup_count;  // far queries identical to rep_q (back of the ovf list)
+    int rep_q;      // first far query of this item, -1 if none
+    float hi[3];
+};
+static_assert(sizeof(GridParams) == 64, "GridParams layout");
+
+struct GridWorkspace {
+    GridParams *params;   // [B]
+    int *ticket;          // [B]   CTAs of the prepare kernel that have finished
+    float *partial;       // [B][MAX_CHUNKS][6]
+    int *tile_sum;        // [B][ntiles]
+    int *cursor;          // [B][maxc + 1]  counts -> exclusive starts -> ends
+    float4 *sorted;       // [B][S]
+    int *ovf;             // [B][Q]
+    size_t maxc, ntiles;
+    size_t bytes;
+};
+
+static size_t max_cells_for(int64_t S)
 {
-    set_error("knn grid search not available in this build");
-    return FFB6D_ERR_INVALID;
+    size_t m = (size_t)S * 8;
+    if (m < 4096) m = 4096;
+    if (m > ((size_t)1 << 22)) m = (size_t)1 << 22;
+    return m;
 }
+
+static GridWorkspace carve(void *base, int64_t B, int64_t S, int64_t Q)
+{
+    GridWorkspace w;
+    w.maxc = max_cells_for(S);
+    w.ntiles = (w.maxc + TILE_CELLS - 1) / TILE_CELLS;
+    size_t off = 0;
+    char *p = (char *)base;
+    auto take = [&](size_t bytes) {
+        char *r = p + off;
+        off = align_up(off + bytes, 256);
+        return r;
+    };
+    w.params = (GridParams *)take((size_t)B * sizeof(GridParams));
+    w.ticket = (int *)take((size_t)B * sizeof(int));
+    w.partial = (float *)take((size_t)B * MAX_CHUNKS * 6 * sizeof(float));
+    w.tile_sum = (int *)take((size_t)B * w.ntiles * sizeof(int));
+    w.cursor = (int *)take((size_t)B * (w.maxc + 1) * sizeof(int));
+    w.sorted = (float4 *)take((size_t)B * (size_t)S * sizeof(float4));
+    w.ovf = (int *)take((size_t)B * (size_t)Q * sizeof(int));
+    w.bytes = off;
+    return w;
+}
+
+// The grid pays off once the all-pairs scan is big enough to dwarf its seven small launches.
+static bool grid_worthwhile(int64_t B, int64_t S, int64_t Q, int K)
+{
+    (void)B;
+    (void)K;
+    return S >= 512 && (double)S * (double)Q >= 2.0e5;
+}
+
+size_t knn_grid_workspace_bytes(int64_t B, int64_t S, int64_t Q, int K)
+{
+    if (!grid_worthwhile(B, S, Q, K)) return 0;
+    return carve(nullptr, B, S, Q).bytes;
+}
+
+__device__ __forceinline__ int cell_of(float p, float lo, float inv_h, int n)
+{
+    const int c = (int)floorf((p - lo) * inv_h);
+    return min(max(c, 0), n - 1);
+}
+
+// ------------------------------------------------------------------ A. prepare
+__global__ void __launch_bounds__(PREP_THREADS)
+grid_prepare_kernel(const float *__restrict__ support, int S, int K, int chunk, int nchunks,
+                    int maxc, int ntiles, float cell_scale, int quantile, GridParams *__restrict__ params,
+                    int *__restrict__ ticket, float *__restrict__ partial,
+                    int *__restrict__ tile_sum, int *__restrict__ cursor, size_t cursor_stride)
+{
+    const int b = blockIdx.y;
+    const float *sup = support + (size_t)b * S * 3;
+    const float INF = __int_as_float(0x7f800000);
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    __shared__ float red[6][32];
+    __shared__ float est[N_SAMPLES];
+    __shared__ float est_pick;
+    __shared__ int flag;
+
+    // ---- partial bounding box of this CTA's chunk
+    float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+    const int s_begin = blockIdx.x * chunk, s_end = min(S, s_begin + chunk);
+    for (int s = s_begin + threadIdx.x; s < s_end; s += PREP_THREADS) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const float v = __ldg(sup + (size_t)s * 3 + a);
+            mn[a] = fminf(mn[a], v);
+            mx[a] = fmaxf(mx[a], v);
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
+        }
+        if (lane == 0) {
+            red[a][wid] = mn[a];
+            red[3 + a][wid] = mx[a];
+        }
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float u = red[a][lane], v = red[3 + a][lane];
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, o));
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            }
+            if (lane == 0) {
+                partial[((size_t)b * MAX_CHUNKS + blockIdx.x) * 6 + a] = u;
+                partial[((size_t)b * MAX_CHUNKS + blockIdx.x) * 6 + 3 + a] = v;
+            }
+        }
+    }
+    // ---- the last CTA of this batch item to get here finishes the job
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) flag = (atomicAdd(ticket + b, 1) == nchunks - 1);
+    __syncthreads();
+    if (!flag) return;
+    __threadfence();
+
+    if (wid == 0) {   // full bbox from the partials
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            float u = INF, v = -INF;
+            for (int c = lane; c < nchunks; c += 32) {
+                u = fminf(u, __ldcg(partial + ((size_t)b * MAX_CHUNKS + c) * 6 + a));
+                v = fmaxf(v, __ldcg(partial + ((size_t)b * MAX_CHUNKS + c) * 6 + 3 + a));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) {
+                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, o));
+                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+            }
+            if (lane == 0) {
+                red[a][0] = u;
+                red[3 + a][0] = v;
+            }
+        }
+    }
+
+    // ---- estimate of the K-th neighbour distance: warp w scans a strided subsample of the
+    // support around sample point w and extracts the kk-th smallest distance, where kk points of
+    // the subsample stand for kk*stride >= K points of the full cloud (dimension-free).
+    {
+        const int stride = max((S + 4095) / 4096, (K + 3) / 4);
+        const int kk = max(1, (K + stride - 1) / stride);          // <= 4
+        const int me = (int)((((long long)wid * S) / N_SAMPLES + S / (2 * N_SAMPLES)) % max(S, 1));
+        float r = 0.f;
+        if (S > 1) {
+            const float qx = __ldg(sup + (size_t)me * 3), qy = __ldg(sup + (size_t)me * 3 + 1),
+                        qz = __ldg(sup + (size_t)me * 3 + 2);
+            TopK<4> t4;
+            t4.init();
+            for (int s = lane * stride; s < S; s += 32 * stride) {
+                if (s == me) continue;
+                const float d = ref_sqdist(qx, qy, qz, __ldg(sup + (size_t)s * 3),
+                                           __ldg(sup + (size_t)s * 3 + 1), __ldg(sup + (size_t)s * 3 + 2));
+                if (d < t4.worst()) t4.push_ordered(d, s);
+            }
+            float m = INF;
+            for (int round = 0; round < kk; ++round) {   // pop the warp-wide minimum kk times
+                m = t4.d[0];
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                const unsigned who = __ballot_sync(0xffffffffu, t4.d[0] == m);
+                if (lane == __ffs(who) - 1) {
+                    t4.d[0] = t4.d[1];
+                    t4.d[1] = t4.d[2];
+                    t4.d[2] = t4.d[3];
+                    t4.d[3] = INF;
+                }
+            }
+            // kk*stride-th neighbour measured; scale to the K-th assuming a 2-D sheet
+            r = sqrtf(m) * sqrtf((float)K / (float)(kk * stride));
+        }
+        if (lane == 0) est[wid] = (r == r && r < INF) ? r : 0.f;
+    }
+    __syncthreads();
+    // the `quantile`-th smallest of the 32 estimates (hole pixels give zeros: they rank first)
+    if (wid == 0) {
+        const float mine = est[lane];
+        int rank = 0;
+        for (int j = 0; j < N_SAMPLES; ++j) {
+            const float o = est[j];
+            rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
+        }
+        if (rank == quantile) est_pick = mine;
+    }
+    __syncthreads();
+
+    if (threadIdx.x == 0) {
+        for (int a = 0; a < 3; ++a) {
+            mn[a] = red[a][0];
+            mx[a] = red[3 + a][0];
+        }
+        const float r_est = est_pick;
+
+        GridParams P;
+        float L[3], scale = 0.f;
+        bool finite = true;
+        for (int a = 0; a < 3; ++a) {
+            L[a] = mx[a] - mn[a];
+            finite = finite && isfinite(L[a]) && isfinite(mn[a]);
+            scale = fmaxf(scale, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
+            P.lo[a] = mn[a];
+            P.hi[a] = mx[a];
+        }
+        const float l1 = fmaxf(L[0], fmaxf(L[1], L[2]));
+        const float l3 = fminf(L[0], fminf(L[1], L[2]));
+        const float l2 = L[0] + L[1] + L[2] - l1 - l3;
+        float h = cell_scale * r_est;
+        if (!(h > 0.f)) h = sqrtf((float)K * l1 * l2 / (float)max(S, 1));   // geometric fallback
+        if (!(h > 0.f)) h = l1 * (float)K / (float)max(S, 1);               // points on a line
+        int n[3] = {1, 1, 1};
+        if (finite && h > 0.f && l1 > 0.f) {
+            for (int it = 0; it < 200; ++it) {
+                double prod = 1.0;
+                for (int a = 0; a < 3; ++a) {
+                    const float f = floorf(L[a] / h);
+                    n[a] = (f >= 4.0e6f) ? 4000000 : (int)f + 1;
+                    prod *= (double)n[a];
+                }
+                if (prod <= (double)maxc) break;
+                h *= 1.2f;
+                if (it == 199) n[0] = n[1] = n[2] = 1;
+            }
+        }
+        const bool single = (n[0] == 1 && n[1] == 1 && n[2] == 1);
+        P.h = single ? INF : h;
+        P.inv_h = single ? 0.f : 1.0f / h;
+        P.slack = 1e-5f * (scale + l1) + 1e-30f;
+        P.n[0] = n[0];
+        P.n[1] = n[1];
+        P.n[2] = n[2];
+        P.ncells = n[0] * n[1] * n[2];
+        P.ovf_count = 0;
+        P.dup_count = 0;
+        P.rep_q = -1;
+        params[b] = P;
+        flag = P.ncells;
+        ticket[b] = 0;   // ready for the next call on this workspace
+    }
+    __syncthreads();
+    // zero this item's cell counters (only the cells that exist) and its tile totals
+    const int ncells = flag;
+    int *c = cursor + (size_t)b * cursor_stride;
+    for (int i = threadIdx.x; i < ncells; i += PREP_THREADS) c[i] = 0;
+    for (int i = threadIdx.x; i < ntiles; i += PREP_THREADS) tile_sum[(size_t)b * ntiles + i] = 0;
+}
+
+// ------------------------------------------------------------------ B. count
+__global__ void __launch_bounds__(256)
+grid_count_kernel(const float *__restrict__ support, int S, const GridParams *__restrict__ params,
+                  int *__restrict__ cursor, size_t cursor_stride, int *__restrict__ tile_sum,
+                  int ntiles)
+{
+    __shared__ int tiles[1024];   // per-CTA tile totals (ntiles <= 4M / 4096)
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    const GridParams &P = params[b];
+    const int used = (P.ncells + TILE_CELLS - 1) / TILE_CELLS;
+    for (int i = threadIdx.x; i < used; i += blockDim.x) tiles[i] = 0;
+    __syncthreads();
+    if (s < S) {
+        const float *p = support + ((size_t)b * S + s) * 3;
+        const int cx = cell_of(__ldg(p), P.lo[0], P.inv_h, P.n[0]);
+        const int cy = cell_of(__ldg(p + 1), P.lo[1], P.inv_h, P.n[1]);
+        const int cz = cell_of(__ldg(p + 2), P.lo[2], P.inv_h, P.n[2]);
+        const int cell = (cz * P.n[1] + cy) * P.n[0] + cx;
+        atomicAdd(cursor + (size_t)b * cursor_stride + cell, 1);
+        atomicAdd(&tiles[cell / TILE_CELLS], 1);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < used; i += blockDim.x)
+        if (tiles[i]) atomicAdd(tile_sum + (size_t)b * ntiles + i, tiles[i]);
+}
+
+// ------------------------------------------------------------------ C. exclusive scan, one CTA per tile
+__global__ void __launch_bounds__(1024)
+grid_scan_kernel(const GridParams *__restrict__ params, int *__restrict__ cursor,
+                 size_t cursor_stride, const int *__restrict__ tile_sum, int ntiles)
+{
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int n = params[b].ncells;
+    if (tile * TILE_CELLS >= n) return;
+    int *c = cursor + (size_t)b * cursor_stride + (size_t)tile * TILE_CELLS;
+    const int cnt = min(TILE_CELLS, n - tile * TILE_CELLS);
+    __shared__ int warp_tot[32];
+    __shared__ int base_s;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    if (wid == 0) {   // total of all earlier tiles
+        int acc = 0;
+        for (int t = lane; t < tile; t += 32) acc += tile_sum[(size_t)b * ntiles + t];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) base_s = acc;
+    }
+    const int i = threadIdx.x * 4;
+    int v[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) v[j] = (i + j < cnt) ? c[i + j] : 0;
+    const int t = v[0] + v[1] + v[2] + v[3];
+    int incl = t;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += u;
+    }
+    if (lane == 31) warp_tot[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        int w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int u = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += u;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int run = base_s + (wid ? warp_tot[wid - 1] : 0) + incl - t;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        if (i + j < cnt) c[i + j] = run;
+        run += v[j];
+    }
+}
+
+// ------------------------------------------------------------------ D. scatter
+__global__ void __launch_bounds__(256)
+grid_scatter_kernel(const float *__restrict__ support, int S, const GridParams *__restrict__ params,
+                    int *__restrict__ cursor, size_t cursor_stride, float4 *__restrict__ sorted)
+{
+    const int b = blockIdx.y;
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const GridParams &P = params[b];
+    const float *p = support + ((size_t)b * S + s) * 3;
+    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+    const int cx = cell_of(x, P.lo[0], P.inv_h, P.n[0]);
+    const int cy = cell_of(y, P.lo[1], P.inv_h, P.n[1]);
+    const int cz = cell_of(z, P.lo[2], P.inv_h, P.n[2]);
+    const int pos = atomicAdd(cursor + (size_t)b * cursor_stride + ((size_t)cz * P.n[1] + cy) * P.n[0] + cx, 1);
+    sorted[(size_t)b * S + pos] = make_float4(x, y, z, __int_as_float(s));
+    // after this kernel cursor[c] is the END of cell c; its start is cursor[c-1] (0 for c == 0)
+}
+
+// ------------------------------------------------------------------ E. search
+template <int KCAP, typename IdxT, bool SELF>
+__global__ void __launch_bounds__(128)
+grid_search_kernel(const float *__restrict__ query, int S, int Q, int K, GridParams *params_all,
+                   const int *__restrict__ cursor_all, size_t cursor_stride,
+                   const float4 *__restrict__ sorted_all, IdxT *__restrict__ idx_out,
+                   int *__restrict__ ovf_all)
+{
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q) return;
+    const GridParams Ps = params_all[b];   // 64 B, same address for the whole CTA: L1 broadcast
+    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
+    const float4 *sorted = sorted_all + (size_t)b * S;
+    float qx, qy, qz;
+    int q;   // row of the output this thread produces
+    if (SELF) {  // queries are the support itself: walk them in cell order (coherent warps)
+        const float4 me = sorted[t];
+        qx = me.x;
+        qy = me.y;
+        qz = me.z;
+        q = __float_as_int(me.w);
+    } else {
+        const float *qp = query + ((size_t)b * Q + t) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+        q = t;
+    }
+    const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
+    const float h = Ps.h, slack = Ps.slack;
+    const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
+    const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
+    const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
+    const float INF = __int_as_float(0x7f800000);
+
+    // a query further than RMAX cells outside the support's box cannot be certified by any block
+    const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
+                            fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
+    bool done = false;
+    TopK<KCAP> top;
+    top.init();
+    auto scan_range = [&](int beg, int end) {
+        for (int p = beg; p < end; p += 4) {   // four loads in flight per thread
+            float4 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) c[u] = __ldg(sorted + min(p + u, end - 1));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const float d = ref_sqdist(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+                const int id = __float_as_int(c[u].w);
+                if (p + u < end && top.accepts(d, id)) top.push_any(d, id);
+            }
+        }
+    };
+    auto cells = [&](int row, int a, int b2) {   // points of cells [a, b2] of one x-row
+        const int beg = (row + a > 0) ? __ldg(cell_end + row + a - 1) : 0;
+        scan_range(beg, __ldg(cell_end + row + b2));
+    };
+    const int r_first = (out > (float)RMAX * h) ? RMAX + 1 : 1;
+    int px0 = 1, px1 = 0, py0 = 1, py1 = 0, pz0 = 1, pz1 = 0;   // block already scanned (empty)
+    for (int r = r_first; r <= RMAX && !done; ++r) {
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
+        for (int z = z0; z <= z1; ++z) {
+            for (int y = y0; y <= y1; ++y) {
+                const int row = (z * ny + y) * nx;
+                if (z >= pz0 && z <= pz1 && y >= py0 && y <= py1) {   // row seen before: only its new ends
+                    if (x0 < px0) cells(row, x0, px0 - 1);
+                    if (x1 > px1) cells(row, px1 + 1, x1);
+                } else {
+                    cells(row, x0, x1);
+                }
+            }
+        }
+        px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
+        // distance from the query to the nearest face of the block that still has cells behind it
+        float m = INF;
+        if (x0 > 0) m = fminf(m, qx - (Ps.lo[0] + (float)x0 * h));
+        if (x1 < nx - 1) m = fminf(m, (Ps.lo[0] + (float)(x1 + 1) * h) - qx);
+        if (y0 > 0) m = fminf(m, qy - (Ps.lo[1] + (float)y0 * h));
+        if (y1 < ny - 1) m = fminf(m, (Ps.lo[1] + (float)(y1 + 1) * h) - qy);
+        if (z0 > 0) m = fminf(m, qz - (Ps.lo[2] + (float)z0 * h));
+        if (z1 < nz - 1) m = fminf(m, (Ps.lo[2] + (float)(z1 + 1) * h) - qz);
+        if (m == INF) {
+            done = true;   // the block is the whole grid
+        } else {
+            const float ms = m - slack;
+            const float kth = top.kth(K);   // +inf while fewer than K candidates were seen
+            done = ms > 0.f && kth <= ms * ms * (1.0f - 1e-5f);
+        }
+    }
+    if (done) {
+        IdxT *o = idx_out + ((size_t)b * Q + q) * K;
+#pragma unroll
+        for (int j = 0; j < KCAP; ++j)
+            if (j < K) o[j] = (IdxT)top.i[j];
+        return;
+    }
+    // not certified: hand over to the full scan, unless this query is bit-identical to the
+    // item's first far query (then it only needs a copy of that query's row)
+    GridParams *Pw = params_all + b;
+    int rep = atomicCAS(&Pw->rep_q, -1, q);
+    bool dup = false;
+    if (rep != -1 && rep != q) {
+        const float *rp = query + ((size_t)b * Q + rep) * 3;
+        // float equality: -0.0 == +0.0 (hole pixels carry either sign) and their distances to
+        // every support point are bit-identical; NaN never compares equal
+        dup = (__ldg(rp) == qx) && (__ldg(rp + 1) == qy) && (__ldg(rp + 2) == qz);
+    }
+    if (dup) {
+        const int slot = atomicAdd(&Pw->dup_count, 1);
+        ovf_all[(size_t)b * Q + (Q - 1 - slot)] = q;
+    } else {
+        const int slot = atomicAdd(&Pw->ovf_count, 1);
+        ovf_all[(size_t)b * Q + slot] = q;
+    }
+}
+
+// ------------------------------------------------------------------ E'. search, one WARP per query
+// For 2 <= K <= 32.  The sorted top list lives across the lanes (lane j holds the j-th best
+// (distance, index)); the cell rows of the block are looked up by the lanes in parallel, their
+// point ranges are flattened with a warp prefix sum so every batch of 32 candidates keeps all
+// lanes busy (one coalesced 512-byte read), and candidates enter the list either one by one
+// (shift-insert through shuffles) or, when many qualify, by a bitonic sort + merge.  Compared
+// with one thread per query this removes the divergence between neighbouring queries and gives
+// the small searches of the schedule (48 ... 3072 queries per frame) 32x more parallelism.
+__device__ __forceinline__ bool pair_less(float ad, int ai, float bd, int bi)
+{
+    return ad < bd || (ad == bd && ai < bi);
+}
+
+__device__ __forceinline__ void warp_minmax(float &d, int &i, int j, bool keep_min)
+{
+    const float od = __shfl_xor_sync(0xffffffffu, d, j);
+    const int oi = __shfl_xor_sync(0xffffffffu, i, j);
+    const bool other_less = pair_less(od, oi, d, i);
+    if (other_less == keep_min) {
+        d = od;
+        i = oi;
+    }
+}
+
+// ascending bitonic sort of one (d,i) pair per lane
+__device__ __forceinline__ void warp_sort(float &d, int &i, int lane)
+{
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const bool up = (lane & k) == 0;
+            warp_minmax(d, i, j, ((lane & j) == 0) == up);
+        }
+    }
+}
+
+template <typename IdxT, bool SELF>
+__global__ void __launch_bounds__(256)
+grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K, GridParams *params_all,
+                        const int *__restrict__ cursor_all, size_t cursor_stride,
+                        const float4 *__restrict__ sorted_all, IdxT *__restrict__ idx_out,
+                        int *__restrict__ ovf_all)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (t >= Q) return;   // warp-uniform
+    const GridParams Ps = params_all[b];
+    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
+    const float4 *sorted = sorted_all + (size_t)b * S;
+    float qx, qy, qz;
+    int q;
+    if (SELF) {
+        const float4 me = __ldg(sorted + t);
+        qx = me.x;
+        qy = me.y;
+        qz = me.z;
+        q = __float_as_int(me.w);
+    } else {
+        const float *qp = query + ((size_t)b * Q + t) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+        q = t;
+    }
+    const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
+    const float h = Ps.h, slack = Ps.slack;
+    const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
+    const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
+    const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
+    const float INF = __int_as_float(0x7f800000);
+    const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
+                            fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
+
+    auto margin = [&](int r) {   // distance to the nearest face of block r that has cells behind it
+        float m = INF;
+        if (cx - r > 0) m = fminf(m, qx - (Ps.lo[0] + (float)(cx - r) * h));
+        if (cx + r < nx - 1) m = fminf(m, (Ps.lo[0] + (float)(cx + r + 1) * h) - qx);
+        if (cy - r > 0) m = fminf(m, qy - (Ps.lo[1] + (float)(cy - r) * h));
+        if (cy + r < ny - 1) m = fminf(m, (Ps.lo[1] + (float)(cy + r + 1) * h) - qy);
+        if (cz - r > 0) m = fminf(m, qz - (Ps.lo[2] + (float)(cz - r) * h));
+        if (cz + r < nz - 1) m = fminf(m, (Ps.lo[2] + (float)(cz + r + 1) * h) - qz);
+        return m;
+    };
+
+    float my_d = INF;   // lane j: j-th best so far
+    int my_i = 0;
+    bool done = false;
+    int r = (out > (float)RMAX * h) ? RMAX + 1 : 1;
+    while (r <= RMAX) {
+        my_d = INF;
+        my_i = 0;
+        bool list_empty = true;
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
+        const int nyb = y1 - y0 + 1;
+        const int nrows = nyb * (z1 - z0 + 1);
+        for (int row0 = 0; row0 < nrows; row0 += 32) {
+            const int rr = row0 + lane;
+            int beg = 0, end = 0;
+            if (rr < nrows) {
+                const int row = ((z0 + rr / nyb) * ny + (y0 + rr % nyb)) * nx;
+                beg = (row + x0 > 0) ? __ldg(cell_end + row + x0 - 1) : 0;
+                end = __ldg(cell_end + row + x1);
+            }
+            const int cnt = end - beg;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int excl = incl - cnt;
+            for (int j0 = 0; j0 < total; j0 += 32) {
+                const int j = j0 + lane;
+                int seg = 0;   // number of rows whose inclusive count is <= j
+#pragma unroll
+                for (int step = 16; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, seg + step - 1);
+                    if (v <= j) seg += step;
+                }
+                const int sb = __shfl_sync(FULL, beg, seg);
+                const int se = __shfl_sync(FULL, excl, seg);
+                const bool valid = j < total;
+                float cd = INF;
+                int ci = 0x7fffffff;
+                if (valid) {
+                    const float4 c = __ldg(sorted + sb + (j - se));
+                    cd = ref_sqdist(qx, qy, qz, c.x, c.y, c.z);
+                    ci = __float_as_int(c.w);
+                }
+                if (list_empty) {   // first batch: sort it straight into the list
+                    warp_sort(cd, ci, lane);
+                    my_d = cd;
+                    my_i = (cd < INF) ? ci : 0;
+                    list_empty = false;
+                    continue;
+                }
+                const float thr_d = __shfl_sync(FULL, my_d, K - 1);
+                const int thr_i = __shfl_sync(FULL, my_i, K - 1);
+                const bool acc = valid && pair_less(cd, ci, thr_d, thr_i);
+                unsigned mask = __ballot_sync(FULL, acc);
+                if (__popc(mask) > 12) {
+                    // many newcomers: sort the batch, keep the 32 smallest of list U batch
+                    warp_sort(cd, ci, lane);
+                    const float rd = __shfl_sync(FULL, cd, 31 - lane);
+                    const int ri = __shfl_sync(FULL, ci, 31 - lane);
+                    if (pair_less(rd, ri, my_d, my_i)) {
+                        my_d = rd;
+                        my_i = ri;
+                    }
+#pragma unroll
+                    for (int jj = 16; jj > 0; jj >>= 1) warp_minmax(my_d, my_i, jj, (lane & jj) == 0);
+                    if (!(my_d < INF)) my_i = 0;
+                } else {
+                    while (mask) {   // shift-insert one candidate
+                        const int src = __ffs(mask) - 1;
+                        mask &= mask - 1;
+                        const float xd = __shfl_sync(FULL, cd, src);
+                        const int xi = __shfl_sync(FULL, ci, src);
+                        const float pd = __shfl_up_sync(FULL, my_d, 1);
+                        const int pi = __shfl_up_sync(FULL, my_i, 1);
+                        const bool gt = pair_less(xd, xi, my_d, my_i);               // mine sorts after x
+                        const bool pgt = lane > 0 && pair_less(xd, xi, pd, pi);      // so does my predecessor
+                        if (gt) {
+                            my_d = pgt ? pd : xd;
+                            my_i = pgt ? pi : xi;
+                        }
+                    }
+                }
+            }
+        }
+        const float m = margin(r);
+        const float kth = __shfl_sync(FULL, my_d, K - 1);
+        if (m == INF) {
+            done = true;
+            break;
+        }
+        const float ms = m - slack;
+        if (ms > 0.f && kth <= ms * ms * (1.0f - 1e-5f)) {
+            done = true;
+            break;
+        }
+        // next ring: the K-th distance found so far bounds the true one, so jump to the first
+        // block whose margin covers it
+        int rn = r + 1;
+        if (kth < INF) {
+            const float need = sqrtf(kth) * (1.0f + 1e-4f) + slack;
+            while (rn <= RMAX && margin(rn) < need) ++rn;
+        }
+        r = rn;
+    }
+    if (done) {
+        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)my_i;
+        return;
+    }
+    if (lane == 0) {
+        GridParams *Pw = params_all + b;
+        const int rep = atomicCAS(&Pw->rep_q, -1, q);
+        bool dup = false;
+        if (rep != -1 && rep != q) {
+            const float *rp = query + ((size_t)b * Q + rep) * 3;
+            dup = (__ldg(rp) == qx) && (__ldg(rp + 1) == qy) && (__ldg(rp + 2) == qz);
+        }
+        if (dup) {
+            const int slot = atomicAdd(&Pw->dup_count, 1);
+            ovf_all[(size_t)b * Q + (Q - 1 - slot)] = q;
+        } else {
+            const int slot = atomicAdd(&Pw->ovf_count, 1);
+            ovf_all[(size_t)b * Q + slot] = q;
+        }
+    }
+}
+
+// ------------------------------------------------------------------ F. overflow: tiled full scan
+template <int KCAP, int THREADS, int TILE, typename IdxT>
+__global__ void __launch_bounds__(THREADS)
+grid_overflow_kernel(const float *__restrict__ support, const float *__restrict__ query, int S,
+                     int Q, int K, const GridParams *__restrict__ params_all,
+                     const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
+{
+    const int b = blockIdx.y;
+    const int count = params_all[b].ovf_count;
+    __shared__ float4 tile[TILE];
+    const float *sup = support + (size_t)b * S * 3;
+    for (int first = blockIdx.x * THREADS; first < count; first += gridDim.x * THREADS) {  // CTA-uniform
+        const int t = first + threadIdx.x;
+        const bool active = t < count;
+        int q = 0;
+        float qx = 0.f, qy = 0.f, qz = 0.f;
+        if (active) {
+            q = ovf_all[(size_t)b * Q + t];
+            const float *qp = query + ((size_t)b * Q + q) * 3;
+            qx = __ldg(qp);
+            qy = __ldg(qp + 1);
+            qz = __ldg(qp + 2);
+        }
+        TopK<KCAP> top;
+        top.init();
+        for (int s0 = 0; s0 < S; s0 += TILE) {
+            const int n = min(TILE, S - s0);
+            __syncthreads();
+            const float *src = sup + (size_t)s0 * 3;
+            for (int i = threadIdx.x; i < 3 * n; i += THREADS)
+                reinterpret_cast<float *>(tile)[(i / 3) * 4 + (i % 3)] = __ldg(src + i);
+            __syncthreads();
+            if (active) {
+#pragma unroll 4
+                for (int i = 0; i < n; ++i) {
+                    const float4 p = tile[i];
+                    const float d = ref_sqdist(qx, qy, qz, p.x, p.y, p.z);
+                    if (d < top.worst()) top.push_ordered(d, s0 + i);
+                }
+            }
+        }
+        if (active) {
+            IdxT *o = idx_out + ((size_t)b * Q + q) * K;
+#pragma unroll
+            for (int j = 0; j < KCAP; ++j)
+                if (j < K) o[j] = (IdxT)top.i[j];
+        }
+    }
+}
+
+// ------------------------------------------------------------------ G. rows of duplicate far queries
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+grid_dup_copy_kernel(int Q, int K, const GridParams *__restrict__ params_all,
+                     const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
+{
+    const int b = blockIdx.y;
+    const int count = params_all[b].dup_count;
+    const int rep = params_all[b].rep_q;
+    if (count == 0) return;
+    const IdxT *src = idx_out + ((size_t)b * Q + rep) * K;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count * K; t += gridDim.x * blockDim.x) {
+        const int q = ovf_all[(size_t)b * Q + (Q - 1 - t / K)];
+        idx_out[((size_t)b * Q + q) * K + t % K] = src[t % K];
+    }
+}
+
+// ------------------------------------------------------------------ host
+static bool g_force_thread_search = false;   // FFB6D_GRID_THREAD_SEARCH=1: one thread per query for every K
+
+template <int KCAP, typename IdxT>
+static int launch_search(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
+                         int K, void *idx_out, const GridWorkspace &w, cudaStream_t st)
+{
+    const bool self = (support == query) && (S == Q);
+    dim3 grid((unsigned)ceil_div(Q, 128), (unsigned)B);
+    if (K >= 2 && K <= 32 && !g_force_thread_search) {
+        dim3 wgrid((unsigned)ceil_div(Q, 8), (unsigned)B);
+        if (self)
+            grid_search_warp_kernel<IdxT, true><<<wgrid, 256, 0, st>>>(
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
+        else
+            grid_search_warp_kernel<IdxT, false><<<wgrid, 256, 0, st>>>(
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
+    } else if (self)
+        grid_search_kernel<KCAP, IdxT, true><<<grid, 128, 0, st>>>(
+            query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
+    else
+        grid_search_kernel<KCAP, IdxT, false><<<grid, 128, 0, st>>>(
+            query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
+    FFB6D_LAUNCH_OK("grid_search_kernel");
+    constexpr int OT = (KCAP >= 32) ? 64 : 128;
+    // sized for a fraction of the queries; chunks beyond that are picked up by the stride loop
+    const int64_t per_item = std::max<int64_t>(1, 4 * kNumSMs / B);
+    dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, OT), per_item), (unsigned)B);
+    grid_overflow_kernel<KCAP, OT, 1024, IdxT><<<ogrid, OT, 0, st>>>(
+        support, query, (int)S, (int)Q, K, w.params, w.ovf, (IdxT *)idx_out);
+    FFB6D_LAUNCH_OK("grid_overflow_kernel");
+    dim3 dgrid((unsigned)std::min<int64_t>(ceil_div(Q * K, 256), per_item), (unsigned)B);
+    grid_dup_copy_kernel<IdxT><<<dgrid, 256, 0, st>>>((int)Q, K, w.params, w.ovf, (IdxT *)idx_out);
+    FFB6D_LAUNCH_OK("grid_dup_copy_kernel");
+    return FFB6D_OK;
+}
+
+template <typename IdxT>
+static int launch_search_k(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
+                           int K, void *idx_out, const GridWorkspace &w, cudaStream_t st)
+{
+    if (K == 1) return launch_search<1, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+    if (K <= 4) return launch_search<4, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+    if (K <= 8) return launch_search<8, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+    if (K <= 16) return launch_search<16, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+    if (K <= 32) return launch_search<32, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+    return launch_search<64, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+}
+
+static float g_cell_scale = 1.0f;
+static int g_quantile = 17;
+static bool g_scale_read = false;
+
+int knn_grid_launch(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
+                    void *idx_out, int idx_is_i64, void *workspace, size_t workspace_bytes,
+                    cudaStream_t st)
+{
+    if (!g_scale_read) {   // tuning knob for experiments; results never depend on it
+        if (const char *e = getenv("FFB6D_GRID_SCALE")) g_cell_scale = (float)atof(e);
+        if (const char *e = getenv("FFB6D_GRID_THREAD_SEARCH")) g_force_thread_search = atoi(e) != 0;
+        if (const char *e = getenv("FFB6D_GRID_QUANTILE")) g_quantile = std::min(31, std::max(0, atoi(e)));
+        g_scale_read = true;
+    }
+    GridWorkspace w = carve(workspace, B, S, Q);
+    if (workspace_bytes < w.bytes) {
+        set_error("knn grid: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+        return FFB6D_ERR_WORKSPACE;
+    }
+    const size_t stride = w.maxc + 1;
+    FFB6D_CUDA(cudaMemsetAsync(w.ticket, 0, (size_t)B * sizeof(int), st));
+    int chunk = 8192;
+    if (ceil_div(S, chunk) > MAX_CHUNKS) chunk = (int)ceil_div(S, MAX_CHUNKS);
+    const int nchunks = (int)ceil_div(S, chunk);
+    grid_prepare_kernel<<<dim3((unsigned)nchunks, (unsigned)B), PREP_THREADS, 0, st>>>(
+        support, (int)S, K, chunk, nchunks, (int)w.maxc, (int)w.ntiles, g_cell_scale, g_quantile, w.params,
+        w.ticket, w.partial, w.tile_sum, w.cursor, stride);
+    FFB6D_LAUNCH_OK("grid_prepare_kernel");
+    dim3 pgrid((unsigned)ceil_div(S, 256), (unsigned)B);
+    grid_count_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, stride, w.tile_sum,
+                                             (int)w.ntiles);
+    FFB6D_LAUNCH_OK("grid_count_kernel");
+    grid_scan_kernel<<<dim3((unsigned)w.ntiles, (unsigned)B), 1024, 0, st>>>(w.params, w.cursor, stride,
+                                                                             w.tile_sum, (int)w.ntiles);
+    FFB6D_LAUNCH_OK("grid_scan_kernel");
+    grid_scatter_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, stride, w.sorted);
+    FFB6D_LAUNCH_OK("grid_scatter_kernel");
+    if (idx_is_i64) return launch_search_k<long long>(support, query, B, S, Q, K, idx_out, w, st);
+    return launch_search_k<int>(support, query, B, S, Q, K, idx_out, w, st);
+}
+
 }  // namespace ffb6d

@@ -14,6 +14,9 @@ import torch
 from . import _lib
 from ._lib import lib, check, LAYOUT_NCS, LAYOUT_NSC
 
+import os as _os
+_DEBUG_GRID = bool(_os.environ.get("FFB6D_DEBUG_GRID"))   # keep KNN workspaces for tools/grid_debug.py
+_debug_ws = []
 _I64 = (torch.int64,)
 _IDX = (torch.int32, torch.int64)
 
@@ -85,6 +88,8 @@ def knn_search(support_pts, query_pts, k, out_dtype=None, algo=0):
         check(lib.ffb6d_knn_batch_algo(sup.data_ptr(), qry.data_ptr(), B, S, Q, k, out.data_ptr(),
                                        int(dt == torch.int64), ws.data_ptr() if ws is not None else None,
                                        ws_bytes, int(algo), _stream(sup.device)))
+    if _DEBUG_GRID:
+        _debug_ws.append((B, S, Q, k, ws))
     return out
 
 

@@ -24,11 +24,12 @@ class FusionPass:
     """
 
     def __init__(self, batch, n_points=12288, h=480, w=640, k=S.K_NEIGH, device="cuda",
-                 layout="nchw", seed=0, index_dtype=torch.int32):
+                 layout="nchw", seed=0, index_dtype=torch.int32, n_streams=4):
         self.B, self.n_points, self.h, self.w, self.k = batch, n_points, h, w, k
         self.device = torch.device(device)
         self.layout = layout
         self.index_dtype = index_dtype
+        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1 else None
         self.gathers = S.gather_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.features = []
@@ -47,27 +48,81 @@ class FusionPass:
     # -- the two halves of a pass ------------------------------------------------------
     def build_indices(self, cld, dpt_xyz, choose, timer=None):
         inputs = S.build_ffb6d_indices(cld, dpt_xyz, k=self.k, index_dtype=self.index_dtype,
-                                       timer=timer)
+                                       timer=timer, streams=self.streams)
         inputs["choose"] = choose
         return inputs
 
+    def _gather(self, op, C, feat, idx):
+        if op == "random_sample":
+            return ops.random_sample(feat, idx)
+        if op == "nearest_interpolation":
+            return ops.nearest_interpolation(feat, idx)
+        return ops.choose_gather(feat.reshape(self.B, C, self.h, self.w) if self.layout == "nchw"
+                                 else feat.squeeze(3), idx)
+
     def run_gathers(self, inputs, timer=None):
-        outs = []
-        for (op, key, C, Sz, Q, K), feat in zip(self.gathers, self.features):
-            idx = inputs[key]
-            if timer is not None:
-                timer.start("gather:%s" % key, S.gather_alg_bytes(C, Sz, Q, idx.shape[-1] if op != "choose" else 1) * self.B)
-            if op == "random_sample":
-                o = ops.random_sample(feat, idx)
-            elif op == "nearest_interpolation":
-                o = ops.nearest_interpolation(feat, idx)
-            else:
-                o = ops.choose_gather(feat.reshape(self.B, C, self.h, self.w) if self.layout == "nchw"
-                                      else feat.squeeze(3), idx)
-            if timer is not None:
-                timer.stop()
-            outs.append(o)
+        n = len(self.gathers)
+        outs = [None] * n
+        if self.streams is None or timer is not None:
+            for i, ((op, key, C, Sz, Q, K), feat) in enumerate(zip(self.gathers, self.features)):
+                idx = inputs[key]
+                if timer is not None:
+                    timer.start("gather:%s" % key,
+                                S.gather_alg_bytes(C, Sz, Q, idx.shape[-1] if op != "choose" else 1) * self.B)
+                outs[i] = self._gather(op, C, feat, idx)
+                if timer is not None:
+                    timer.stop()
+            return outs
+        # the 23 gathers are independent of each other too
+        main = torch.cuda.current_stream(self.device)
+        order = sorted(range(n), key=lambda i: -(self.gathers[i][2] * self.gathers[i][4]))
+        for st in self.streams:
+            st.wait_stream(main)
+        for j, i in enumerate(order):
+            op, key, C, Sz, Q, K = self.gathers[i]
+            with torch.cuda.stream(self.streams[j % len(self.streams)]):
+                outs[i] = self._gather(op, C, self.features[i], inputs[key])
+        for st in self.streams:
+            main.wait_stream(st)
         return outs
+
+    # -- CUDA-graph replay: the pass is ~200 small launches with static shapes ----------
+    def capture(self, cld, dpt_xyz, choose, host_inputs=None, digest=None):
+        """Capture one pass into a CUDA graph and return ``replay()``.
+
+        ``cld/dpt_xyz/choose`` are the static device buffers the graph reads.  With
+        ``host_inputs=(cld_h, xyz_h, choose_h)`` (pinned) the graph starts with the three H2D
+        copies, and with ``digest=(fn, pinned_out)`` it ends with ``pinned_out.copy_(fn(inputs,
+        outs))`` -- the end-to-end variant bench.py times.  ``replay()`` returns (inputs, outs)
+        of the captured pass (tensors owned by the graph's memory pool)."""
+        def body():
+            if host_inputs is not None:
+                cld.copy_(host_inputs[0], non_blocking=True)
+                dpt_xyz.copy_(host_inputs[1], non_blocking=True)
+                choose.copy_(host_inputs[2], non_blocking=True)
+            res = self(cld, dpt_xyz, choose)
+            if digest is not None:
+                d = digest[0](*res)
+                digest[1][: d.numel()].copy_(d, non_blocking=True)
+            return res
+
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(side):
+            for _ in range(2):        # allocator + lazy one-time settings happen outside the capture
+                body()
+        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            res = body()
+
+        def replay():
+            graph.replay()
+            return res
+
+        replay.graph = graph
+        return replay
 
     def __call__(self, cld, dpt_xyz, choose, timer=None):
         """cld [B,N0,3] f32, dpt_xyz [B,H,W,3] f32, choose [B,1,N0] int -> (inputs dict, outputs)."""

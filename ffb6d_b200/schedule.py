@@ -113,11 +113,12 @@ def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
     return pyr
 
 
-def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=None):
+def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None):
     """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
 
     :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
     :param dpt_xyz: ``[B, H, W, 3]`` float32 CUDA, the organised cloud (zero rows at holes)
+    :param streams: optional list of side ``torch.cuda.Stream`` s to overlap the 22 searches on
     :param timer: optional object with ``start(name, alg_bytes)`` / ``stop()`` called around
       every KNN call (bench.py's per-op CUDA-event timer)
     :return: dict with the reference's keys (ycb_dataset.py:283-309), each with a leading
@@ -144,13 +145,27 @@ def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=
         if i < N_DS_LAYERS:
             n //= PCLD_SUB_S_R[i]
     inputs = {}
-    for key, s, q, kk in knn_schedule(n0, H, W, k):
-        sup, qry = sets[s], sets[q]
-        if timer is not None:
-            timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
-        inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype)
-        if timer is not None:
-            timer.stop()
+    calls = knn_schedule(n0, H, W, k)
+    if streams is None or timer is not None:
+        for key, s, q, kk in calls:
+            sup, qry = sets[s], sets[q]
+            if timer is not None:
+                timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
+            inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype)
+            if timer is not None:
+                timer.stop()
+    else:
+        # the 22 searches are independent: spread them over side streams (biggest first) so the
+        # many small launches overlap instead of queueing behind each other
+        main = torch.cuda.current_stream(cld.device)
+        order = sorted(calls, key=lambda c: -(sets[c[1]].shape[1] + sets[c[2]].shape[1] * c[3]))
+        for st in streams:
+            st.wait_stream(main)
+        for i, (key, s, q, kk) in enumerate(order):
+            with torch.cuda.stream(streams[i % len(streams)]):
+                inputs[key] = knn_search(sets[s], sets[q], kk, out_dtype=index_dtype)
+        for st in streams:
+            main.wait_stream(st)
     for i in range(N_DS_LAYERS):
         inputs["cld_xyz%d" % i] = sets[("cld", i)]
         n_sub = sets[("cld", i + 1)].shape[1]
