@@ -220,6 +220,8 @@ def load_ncu_traffic():
 def kernel_family(op_name):
     """Map a timed op to the kernel function that runs it."""
     kind, key = op_name.split(":", 1)
+    if kind == "knn_build":
+        return "knn_k1" if key.endswith(":k1") else "knn_k16"
     if kind == "knn":
         return "knn_k1" if ("interp" in key or key.startswith("p2r")) else "knn_k16"
     return "gather_k1" if (key.startswith("p2r") or "interp" in key or key == "choose") else "gather_max_k16"
@@ -268,7 +270,8 @@ def main():
 
     B, N0 = args.batch, args.n_points
     # ---- synthetic inputs: distinct frames per rank, pinned on the host + resident on the device
-    batch = make_batch(range(rank * B, rank * B + B), n_points=N0)
+    from ffb6d_b200.dist import frame_shard, max_over_ranks, sum_over_ranks
+    batch = make_batch(frame_shard(B, rank, world), n_points=N0)
     cld_h = torch.from_numpy(batch["cld"]).pin_memory()
     xyz_h = torch.from_numpy(batch["dpt_xyz"]).pin_memory()
     cho_h = torch.from_numpy(batch["choose"]).pin_memory()
@@ -373,14 +376,9 @@ def main():
         inst_ms += i0.elapsed_time(i1)
     clocks = sampler.stop() if sampler is not None else None
 
-    # ---- max over ranks
-    if dist is not None:
-        tt = torch.tensor([ms, e2e_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        ms, e2e_ms = tt.tolist()
-        ll = torch.tensor([launches], device=dev, dtype=torch.int64)
-        dist.all_reduce(ll, op=dist.ReduceOp.SUM)
-        launches = int(ll.item())
+    # ---- max over ranks (device time, never wall clock of one rank)
+    ms, e2e_ms = max_over_ranks([ms, e2e_ms], device=dev)
+    launches = sum_over_ranks(int(launches), device=dev)
 
     if rank != 0:
         if dist is not None:

@@ -130,6 +130,41 @@ int ffb6d_knn_batch_algo(const float *support, const float *query, int64_t B, in
                         workspace_bytes, algo, (cudaStream_t)stream);
 }
 
+size_t ffb6d_knn_grid_bytes(int64_t B, int64_t S)
+{
+    if (B <= 0 || S <= 0) return 0;
+    return knn_grid_store_bytes(B, S);
+}
+
+size_t ffb6d_knn_grid_query_bytes(int64_t B, int64_t Q)
+{
+    if (B <= 0 || Q <= 0) return 0;
+    return knn_grid_query_bytes(B, Q);
+}
+
+int ffb6d_knn_grid_build(const float *support, int64_t B, int64_t S, int K_hint, void *grid,
+                         size_t grid_bytes, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 1 && S >= 1 && B < 65536 && S < (1ll << 31), "knn_grid_build: bad size");
+    FFB6D_CHECK_ARG(K_hint >= 1 && K_hint <= FFB6D_MAX_K, "knn_grid_build: K_hint=%d outside [1,%d]",
+                    K_hint, FFB6D_MAX_K);
+    FFB6D_CHECK_ARG(support && grid, "knn_grid_build: null pointer");
+    return knn_grid_build(support, B, S, K_hint, grid, grid_bytes, (cudaStream_t)stream);
+}
+
+int ffb6d_knn_grid_query(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
+                         int K, void *idx_out, int idx_is_i64, const void *grid, size_t grid_bytes,
+                         void *scratch, size_t scratch_bytes, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && S >= 1 && Q >= 0 && B < 65536 && S < (1ll << 31) && Q < (1ll << 31),
+                    "knn_grid_query: bad size");
+    FFB6D_CHECK_ARG(K >= 1 && K <= FFB6D_MAX_K, "knn_grid_query: K=%d outside [1,%d]", K, FFB6D_MAX_K);
+    if (B == 0 || Q == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(support && query && idx_out && grid && scratch, "knn_grid_query: null pointer");
+    return knn_grid_query(support, query, B, S, Q, K, idx_out, idx_is_i64, grid, grid_bytes, scratch,
+                          scratch_bytes, (cudaStream_t)stream);
+}
+
 int ffb6d_knn_batch_host(const float *batch_data, size_t batch_size, size_t npts, size_t dim,
                          const float *queries, size_t nqueries, size_t K, long *batch_indices)
 {

@@ -81,9 +81,17 @@ struct TopK {
 // entry points of the two search algorithms (knn_brute.cu, knn_grid.cu)
 int knn_brute_launch(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
                      int K, void *idx_out, int idx_is_i64, cudaStream_t st);
-size_t knn_grid_workspace_bytes(int64_t B, int64_t S, int64_t Q, int K);
+size_t knn_grid_workspace_bytes(int64_t B, int64_t S, int64_t Q, int K);   // 0: the grid declines
 int knn_grid_launch(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
                     int K, void *idx_out, int idx_is_i64, void *workspace, size_t workspace_bytes,
                     cudaStream_t st);
+// build once, query many times (knn_grid.cu)
+size_t knn_grid_store_bytes(int64_t B, int64_t S);
+size_t knn_grid_query_bytes(int64_t B, int64_t Q);
+int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid_mem,
+                   size_t grid_bytes, cudaStream_t st);
+int knn_grid_query(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
+                   void *idx_out, int idx_is_i64, const void *grid_mem, size_t grid_bytes,
+                   void *scratch, size_t scratch_bytes, cudaStream_t st);
 
 }  // namespace ffb6d

@@ -50,22 +50,36 @@ struct __align__(16) GridParams {
     float slack;    // absolute safety margin of the stop test
     int n[3];       // cells per axis
     int ncells;
-    int ovf_count;  // queries handed to the overflow pass (front of the ovf list)
-    int dup_count;  // far queries identical to rep_q (back of the ovf list)
-    int rep_q;      // first far query of this item, -1 if none
     float hi[3];
+    int pad[3];
 };
 static_assert(sizeof(GridParams) == 64, "GridParams layout");
 
-struct GridWorkspace {
+// per batch item, per query call: who could not be certified by the grid
+struct __align__(16) QueryState {
+    int ovf_count;  // queries handed to the overflow pass (front of the ovf list)
+    int dup_count;  // far queries equal to rep_q (back of the ovf list)
+    int rep_q;      // 1 + first far query of this item, 0 if none
+    int pad;
+};
+
+// The grid of one support batch: written by knn_grid_build, read-only afterwards, so any
+// number of query calls (on any stream ordered after the build) can share it.
+struct GridStore {
     GridParams *params;   // [B]
     int *ticket;          // [B]   CTAs of the prepare kernel that have finished
     float *partial;       // [B][MAX_CHUNKS][6]
     int *tile_sum;        // [B][ntiles]
-    int *cursor;          // [B][maxc + 1]  counts -> exclusive starts -> ends
+    int *cursor;          // [B][maxc]  counts -> exclusive starts -> ends
     float4 *sorted;       // [B][S]
-    int *ovf;             // [B][Q]
     size_t maxc, ntiles;
+    size_t bytes;
+};
+
+// scratch of one query call
+struct QueryScratch {
+    QueryState *state;    // [B]
+    int *ovf;             // [B][Q]
     size_t bytes;
 };
 
@@ -74,12 +88,12 @@ static size_t max_cells_for(int64_t S)
     size_t m = (size_t)S * 8;
     if (m < 4096) m = 4096;
     if (m > ((size_t)1 << 22)) m = (size_t)1 << 22;
-    return m;
+    return (m + TILE_CELLS - 1) / TILE_CELLS * TILE_CELLS;   // whole scan tiles, 16-byte aligned rows
 }
 
-static GridWorkspace carve(void *base, int64_t B, int64_t S, int64_t Q)
+static GridStore carve_grid(void *base, int64_t B, int64_t S)
 {
-    GridWorkspace w;
+    GridStore w;
     w.maxc = max_cells_for(S);
     w.ntiles = (w.maxc + TILE_CELLS - 1) / TILE_CELLS;
     size_t off = 0;
@@ -93,12 +107,27 @@ static GridWorkspace carve(void *base, int64_t B, int64_t S, int64_t Q)
     w.ticket = (int *)take((size_t)B * sizeof(int));
     w.partial = (float *)take((size_t)B * MAX_CHUNKS * 6 * sizeof(float));
     w.tile_sum = (int *)take((size_t)B * w.ntiles * sizeof(int));
-    w.cursor = (int *)take((size_t)B * (w.maxc + 1) * sizeof(int));
+    w.cursor = (int *)take((size_t)B * w.maxc * sizeof(int));
     w.sorted = (float4 *)take((size_t)B * (size_t)S * sizeof(float4));
-    w.ovf = (int *)take((size_t)B * (size_t)Q * sizeof(int));
     w.bytes = off;
     return w;
 }
+
+static QueryScratch carve_query(void *base, int64_t B, int64_t Q)
+{
+    QueryScratch w;
+    size_t off = 0;
+    char *p = (char *)base;
+    w.state = (QueryState *)(p + off);
+    off = align_up(off + (size_t)B * sizeof(QueryState), 256);
+    w.ovf = (int *)(p + off);
+    off = align_up(off + (size_t)B * (size_t)Q * sizeof(int), 256);
+    w.bytes = off;
+    return w;
+}
+
+size_t knn_grid_store_bytes(int64_t B, int64_t S) { return carve_grid(nullptr, B, S).bytes; }
+size_t knn_grid_query_bytes(int64_t B, int64_t Q) { return carve_query(nullptr, B, Q).bytes; }
 
 // The grid pays off once the all-pairs scan is big enough to dwarf its seven small launches.
 static bool grid_worthwhile(int64_t B, int64_t S, int64_t Q, int K)
@@ -111,7 +140,7 @@ static bool grid_worthwhile(int64_t B, int64_t S, int64_t Q, int K)
 size_t knn_grid_workspace_bytes(int64_t B, int64_t S, int64_t Q, int K)
 {
     if (!grid_worthwhile(B, S, Q, K)) return 0;
-    return carve(nullptr, B, S, Q).bytes;
+    return knn_grid_store_bytes(B, S) + knn_grid_query_bytes(B, Q);
 }
 
 __device__ __forceinline__ int cell_of(float p, float lo, float inv_h, int n)
@@ -124,8 +153,7 @@ __device__ __forceinline__ int cell_of(float p, float lo, float inv_h, int n)
 __global__ void __launch_bounds__(PREP_THREADS)
 grid_prepare_kernel(const float *__restrict__ support, int S, int K, int chunk, int nchunks,
                     int maxc, int ntiles, float cell_scale, int quantile, GridParams *__restrict__ params,
-                    int *__restrict__ ticket, float *__restrict__ partial,
-                    int *__restrict__ tile_sum, int *__restrict__ cursor, size_t cursor_stride)
+                    int *__restrict__ ticket, float *__restrict__ partial)
 {
     const int b = blockIdx.y;
     const float *sup = support + (size_t)b * S * 3;
@@ -216,11 +244,21 @@ grid_prepare_kernel(const float *__restrict__ support, int S, int K, int chunk, 
                         qz = __ldg(sup + (size_t)me * 3 + 2);
             TopK<4> t4;
             t4.init();
-            for (int s = lane * stride; s < S; s += 32 * stride) {
-                if (s == me) continue;
-                const float d = ref_sqdist(qx, qy, qz, __ldg(sup + (size_t)s * 3),
-                                           __ldg(sup + (size_t)s * 3 + 1), __ldg(sup + (size_t)s * 3 + 2));
-                if (d < t4.worst()) t4.push_ordered(d, s);
+            for (int s0 = lane * stride; s0 < S; s0 += 4 * 32 * stride) {   // 12 loads in flight
+                float px[4], py[4], pz[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int s = min(s0 + u * 32 * stride, S - 1);
+                    px[u] = __ldg(sup + (size_t)s * 3);
+                    py[u] = __ldg(sup + (size_t)s * 3 + 1);
+                    pz[u] = __ldg(sup + (size_t)s * 3 + 2);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int s = s0 + u * 32 * stride;
+                    const float d = ref_sqdist(qx, qy, qz, px[u], py[u], pz[u]);
+                    if (s < S && s != me && d < t4.worst()) t4.push_ordered(d, s);
+                }
             }
             float m = INF;
             for (int round = 0; round < kk; ++round) {   // pop the warp-wide minimum kk times
@@ -298,19 +336,24 @@ grid_prepare_kernel(const float *__restrict__ support, int S, int K, int chunk, 
         P.n[1] = n[1];
         P.n[2] = n[2];
         P.ncells = n[0] * n[1] * n[2];
-        P.ovf_count = 0;
-        P.dup_count = 0;
-        P.rep_q = -1;
+        for (int a = 0; a < 3; ++a) P.pad[a] = 0;
         params[b] = P;
-        flag = P.ncells;
-        ticket[b] = 0;   // ready for the next call on this workspace
+        ticket[b] = 0;   // ready for the next build on this storage
     }
-    __syncthreads();
-    // zero this item's cell counters (only the cells that exist) and its tile totals
-    const int ncells = flag;
-    int *c = cursor + (size_t)b * cursor_stride;
-    for (int i = threadIdx.x; i < ncells; i += PREP_THREADS) c[i] = 0;
-    for (int i = threadIdx.x; i < ntiles; i += PREP_THREADS) tile_sum[(size_t)b * ntiles + i] = 0;
+}
+
+// ------------------------------------------------------------------ A'. zero the cell counters that exist
+__global__ void __launch_bounds__(256)
+grid_zero_kernel(const GridParams *__restrict__ params, int *__restrict__ cursor, size_t cursor_stride,
+                 int *__restrict__ tile_sum, int ntiles)
+{
+    const int b = blockIdx.y, tile = blockIdx.x;
+    const int n = params[b].ncells;
+    if (tile * TILE_CELLS >= n) return;
+    int4 *c = reinterpret_cast<int4 *>(cursor + (size_t)b * cursor_stride + (size_t)tile * TILE_CELLS);
+    // whole tiles are zeroed (the budget is a multiple of the tile): simpler and still tiny
+    for (int i = threadIdx.x; i < TILE_CELLS / 4; i += blockDim.x) c[i] = make_int4(0, 0, 0, 0);
+    if (threadIdx.x == 0) tile_sum[(size_t)b * ntiles + tile] = 0;
 }
 
 // ------------------------------------------------------------------ B. count
@@ -413,10 +456,10 @@ grid_scatter_kernel(const float *__restrict__ support, int S, const GridParams *
 // ------------------------------------------------------------------ E. search
 template <int KCAP, typename IdxT, bool SELF>
 __global__ void __launch_bounds__(128)
-grid_search_kernel(const float *__restrict__ query, int S, int Q, int K, GridParams *params_all,
-                   const int *__restrict__ cursor_all, size_t cursor_stride,
-                   const float4 *__restrict__ sorted_all, IdxT *__restrict__ idx_out,
-                   int *__restrict__ ovf_all)
+grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
+                   const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
+                   size_t cursor_stride, const float4 *__restrict__ sorted_all,
+                   IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
 {
     const int b = blockIdx.y;
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -512,8 +555,8 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K, GridPar
     }
     // not certified: hand over to the full scan, unless this query is bit-identical to the
     // item's first far query (then it only needs a copy of that query's row)
-    GridParams *Pw = params_all + b;
-    int rep = atomicCAS(&Pw->rep_q, -1, q);
+    QueryState *Pw = state_all + b;
+    int rep = atomicCAS(&Pw->rep_q, 0, q + 1) - 1;   // stored as q+1 so that all-zero means 'none'
     bool dup = false;
     if (rep != -1 && rep != q) {
         const float *rp = query + ((size_t)b * Q + rep) * 3;
@@ -569,10 +612,10 @@ __device__ __forceinline__ void warp_sort(float &d, int &i, int lane)
 
 template <typename IdxT, bool SELF>
 __global__ void __launch_bounds__(256)
-grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K, GridParams *params_all,
-                        const int *__restrict__ cursor_all, size_t cursor_stride,
-                        const float4 *__restrict__ sorted_all, IdxT *__restrict__ idx_out,
-                        int *__restrict__ ovf_all)
+grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
+                        const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
+                        size_t cursor_stride, const float4 *__restrict__ sorted_all,
+                        IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
 {
     const unsigned FULL = 0xffffffffu;
     const int b = blockIdx.y;
@@ -731,8 +774,8 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K, Gr
         return;
     }
     if (lane == 0) {
-        GridParams *Pw = params_all + b;
-        const int rep = atomicCAS(&Pw->rep_q, -1, q);
+        QueryState *Pw = state_all + b;
+        const int rep = atomicCAS(&Pw->rep_q, 0, q + 1) - 1;   // stored as q+1: all-zero state = 'none'
         bool dup = false;
         if (rep != -1 && rep != q) {
             const float *rp = query + ((size_t)b * Q + rep) * 3;
@@ -752,11 +795,11 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K, Gr
 template <int KCAP, int THREADS, int TILE, typename IdxT>
 __global__ void __launch_bounds__(THREADS)
 grid_overflow_kernel(const float *__restrict__ support, const float *__restrict__ query, int S,
-                     int Q, int K, const GridParams *__restrict__ params_all,
+                     int Q, int K, const QueryState *__restrict__ state_all,
                      const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
 {
     const int b = blockIdx.y;
-    const int count = params_all[b].ovf_count;
+    const int count = state_all[b].ovf_count;
     __shared__ float4 tile[TILE];
     const float *sup = support + (size_t)b * S * 3;
     for (int first = blockIdx.x * THREADS; first < count; first += gridDim.x * THREADS) {  // CTA-uniform
@@ -798,15 +841,83 @@ grid_overflow_kernel(const float *__restrict__ support, const float *__restrict_
     }
 }
 
+// ------------------------------------------------------------------ F'. overflow, one warp per query (K <= 32)
+// Same full scan, but the 32 lanes split the support and share the sorted list of
+// grid_search_warp_kernel: a handful of far queries (typically one per frame once duplicates
+// are folded) no longer costs a serial walk over the whole support by a single thread.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+grid_overflow_warp_kernel(const float *__restrict__ support, const float *__restrict__ query, int S,
+                          int Q, int K, const QueryState *__restrict__ state_all,
+                          const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
+{
+    const unsigned FULL = 0xffffffffu;
+    const int b = blockIdx.y;
+    const int count = state_all[b].ovf_count;
+    const int lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const float *sup = support + (size_t)b * S * 3;
+    const float INF = __int_as_float(0x7f800000);
+    for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < count; t += gridDim.x * wpb) {
+        const int q = ovf_all[(size_t)b * Q + t];
+        const float *qp = query + ((size_t)b * Q + q) * 3;
+        const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
+        float my_d = INF;
+        int my_i = 0;
+        for (int s0 = 0; s0 < S; s0 += 32) {
+            const int sI = s0 + lane;
+            const bool valid = sI < S;
+            float cd = INF;
+            int ci = 0x7fffffff;
+            if (valid) {
+                cd = ref_sqdist(qx, qy, qz, __ldg(sup + (size_t)sI * 3), __ldg(sup + (size_t)sI * 3 + 1),
+                                __ldg(sup + (size_t)sI * 3 + 2));
+                ci = sI;
+            }
+            const float thr_d = __shfl_sync(FULL, my_d, K - 1);
+            const int thr_i = __shfl_sync(FULL, my_i, K - 1);
+            unsigned mask = __ballot_sync(FULL, valid && pair_less(cd, ci, thr_d, thr_i));
+            if (__popc(mask) > 12) {
+                warp_sort(cd, ci, lane);
+                const float rd = __shfl_sync(FULL, cd, 31 - lane);
+                const int ri = __shfl_sync(FULL, ci, 31 - lane);
+                if (pair_less(rd, ri, my_d, my_i)) {
+                    my_d = rd;
+                    my_i = ri;
+                }
+#pragma unroll
+                for (int jj = 16; jj > 0; jj >>= 1) warp_minmax(my_d, my_i, jj, (lane & jj) == 0);
+                if (!(my_d < INF)) my_i = 0;
+            } else {
+                while (mask) {
+                    const int src = __ffs(mask) - 1;
+                    mask &= mask - 1;
+                    const float xd = __shfl_sync(FULL, cd, src);
+                    const int xi = __shfl_sync(FULL, ci, src);
+                    const float pd = __shfl_up_sync(FULL, my_d, 1);
+                    const int pi = __shfl_up_sync(FULL, my_i, 1);
+                    const bool gt = pair_less(xd, xi, my_d, my_i);
+                    const bool pgt = lane > 0 && pair_less(xd, xi, pd, pi);
+                    if (gt) {
+                        my_d = pgt ? pd : xd;
+                        my_i = pgt ? pi : xi;
+                    }
+                }
+            }
+        }
+        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)my_i;
+    }
+}
+
 // ------------------------------------------------------------------ G. rows of duplicate far queries
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
-grid_dup_copy_kernel(int Q, int K, const GridParams *__restrict__ params_all,
+grid_dup_copy_kernel(int Q, int K, const QueryState *__restrict__ state_all,
                      const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
 {
     const int b = blockIdx.y;
-    const int count = params_all[b].dup_count;
-    const int rep = params_all[b].rep_q;
+    const int count = state_all[b].dup_count;
+    const int rep = state_all[b].rep_q - 1;
     if (count == 0) return;
     const IdxT *src = idx_out + ((size_t)b * Q + rep) * K;
     for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < count * K; t += gridDim.x * blockDim.x) {
@@ -817,92 +928,138 @@ grid_dup_copy_kernel(int Q, int K, const GridParams *__restrict__ params_all,
 
 // ------------------------------------------------------------------ host
 static bool g_force_thread_search = false;   // FFB6D_GRID_THREAD_SEARCH=1: one thread per query for every K
+static float g_cell_scale = 1.0f;
+static int g_quantile = 17;
+static bool g_env_read = false;
+
+static void read_env()
+{
+    if (g_env_read) return;   // tuning knobs for experiments; results never depend on them
+    if (const char *e = getenv("FFB6D_GRID_SCALE")) g_cell_scale = (float)atof(e);
+    if (const char *e = getenv("FFB6D_GRID_THREAD_SEARCH")) g_force_thread_search = atoi(e) != 0;
+    if (const char *e = getenv("FFB6D_GRID_QUANTILE")) g_quantile = std::min(31, std::max(0, atoi(e)));
+    g_env_read = true;
+}
 
 template <int KCAP, typename IdxT>
 static int launch_search(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
-                         int K, void *idx_out, const GridWorkspace &w, cudaStream_t st)
+                         int K, void *idx_out, const GridStore &w, const QueryScratch &qs,
+                         cudaStream_t st)
 {
     const bool self = (support == query) && (S == Q);
-    dim3 grid((unsigned)ceil_div(Q, 128), (unsigned)B);
-    if (K >= 2 && K <= 32 && !g_force_thread_search) {
+    const bool warp = K >= 2 && K <= 32 && !g_force_thread_search;
+    FFB6D_CUDA(cudaMemsetAsync(qs.state, 0, (size_t)B * sizeof(QueryState), st));
+    if (warp) {
         dim3 wgrid((unsigned)ceil_div(Q, 8), (unsigned)B);
         if (self)
             grid_search_warp_kernel<IdxT, true><<<wgrid, 256, 0, st>>>(
-                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
         else
             grid_search_warp_kernel<IdxT, false><<<wgrid, 256, 0, st>>>(
-                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
-    } else if (self)
-        grid_search_kernel<KCAP, IdxT, true><<<grid, 128, 0, st>>>(
-            query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
-    else
-        grid_search_kernel<KCAP, IdxT, false><<<grid, 128, 0, st>>>(
-            query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc + 1, w.sorted, (IdxT *)idx_out, w.ovf);
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+    } else {
+        dim3 grid((unsigned)ceil_div(Q, 128), (unsigned)B);
+        if (self)
+            grid_search_kernel<KCAP, IdxT, true><<<grid, 128, 0, st>>>(
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+        else
+            grid_search_kernel<KCAP, IdxT, false><<<grid, 128, 0, st>>>(
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+    }
     FFB6D_LAUNCH_OK("grid_search_kernel");
-    constexpr int OT = (KCAP >= 32) ? 64 : 128;
-    // sized for a fraction of the queries; chunks beyond that are picked up by the stride loop
     const int64_t per_item = std::max<int64_t>(1, 4 * kNumSMs / B);
-    dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, OT), per_item), (unsigned)B);
-    grid_overflow_kernel<KCAP, OT, 1024, IdxT><<<ogrid, OT, 0, st>>>(
-        support, query, (int)S, (int)Q, K, w.params, w.ovf, (IdxT *)idx_out);
+    if (K <= 32) {
+        dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, 8), per_item), (unsigned)B);
+        grid_overflow_warp_kernel<IdxT><<<ogrid, 256, 0, st>>>(support, query, (int)S, (int)Q, K, qs.state,
+                                                               qs.ovf, (IdxT *)idx_out);
+    } else {
+        constexpr int OT = (KCAP >= 32) ? 64 : 128;
+        dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, OT), per_item), (unsigned)B);
+        grid_overflow_kernel<KCAP, OT, 1024, IdxT><<<ogrid, OT, 0, st>>>(
+            support, query, (int)S, (int)Q, K, qs.state, qs.ovf, (IdxT *)idx_out);
+    }
     FFB6D_LAUNCH_OK("grid_overflow_kernel");
     dim3 dgrid((unsigned)std::min<int64_t>(ceil_div(Q * K, 256), per_item), (unsigned)B);
-    grid_dup_copy_kernel<IdxT><<<dgrid, 256, 0, st>>>((int)Q, K, w.params, w.ovf, (IdxT *)idx_out);
+    grid_dup_copy_kernel<IdxT><<<dgrid, 256, 0, st>>>((int)Q, K, qs.state, qs.ovf, (IdxT *)idx_out);
     FFB6D_LAUNCH_OK("grid_dup_copy_kernel");
     return FFB6D_OK;
 }
 
 template <typename IdxT>
 static int launch_search_k(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
-                           int K, void *idx_out, const GridWorkspace &w, cudaStream_t st)
+                           int K, void *idx_out, const GridStore &w, const QueryScratch &qs,
+                           cudaStream_t st)
 {
-    if (K == 1) return launch_search<1, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
-    if (K <= 4) return launch_search<4, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
-    if (K <= 8) return launch_search<8, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
-    if (K <= 16) return launch_search<16, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
-    if (K <= 32) return launch_search<32, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
-    return launch_search<64, IdxT>(support, query, B, S, Q, K, idx_out, w, st);
+    if (K == 1) return launch_search<1, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    if (K <= 4) return launch_search<4, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    if (K <= 8) return launch_search<8, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    if (K <= 16) return launch_search<16, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    if (K <= 32) return launch_search<32, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    return launch_search<64, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
 }
 
-static float g_cell_scale = 1.0f;
-static int g_quantile = 17;
-static bool g_scale_read = false;
-
-int knn_grid_launch(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
-                    void *idx_out, int idx_is_i64, void *workspace, size_t workspace_bytes,
-                    cudaStream_t st)
+// Build the grid of `support` for searches of about K neighbours (K only tunes the cell size).
+int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid_mem,
+                   size_t grid_bytes, cudaStream_t st)
 {
-    if (!g_scale_read) {   // tuning knob for experiments; results never depend on it
-        if (const char *e = getenv("FFB6D_GRID_SCALE")) g_cell_scale = (float)atof(e);
-        if (const char *e = getenv("FFB6D_GRID_THREAD_SEARCH")) g_force_thread_search = atoi(e) != 0;
-        if (const char *e = getenv("FFB6D_GRID_QUANTILE")) g_quantile = std::min(31, std::max(0, atoi(e)));
-        g_scale_read = true;
-    }
-    GridWorkspace w = carve(workspace, B, S, Q);
-    if (workspace_bytes < w.bytes) {
-        set_error("knn grid: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+    read_env();
+    GridStore w = carve_grid(grid_mem, B, S);
+    if (!grid_mem || grid_bytes < w.bytes) {
+        set_error("knn grid build: %zu bytes of grid storage required, %zu given", w.bytes, grid_bytes);
         return FFB6D_ERR_WORKSPACE;
     }
-    const size_t stride = w.maxc + 1;
     FFB6D_CUDA(cudaMemsetAsync(w.ticket, 0, (size_t)B * sizeof(int), st));
     int chunk = 8192;
     if (ceil_div(S, chunk) > MAX_CHUNKS) chunk = (int)ceil_div(S, MAX_CHUNKS);
     const int nchunks = (int)ceil_div(S, chunk);
     grid_prepare_kernel<<<dim3((unsigned)nchunks, (unsigned)B), PREP_THREADS, 0, st>>>(
-        support, (int)S, K, chunk, nchunks, (int)w.maxc, (int)w.ntiles, g_cell_scale, g_quantile, w.params,
-        w.ticket, w.partial, w.tile_sum, w.cursor, stride);
+        support, (int)S, K, chunk, nchunks, (int)w.maxc, (int)w.ntiles, g_cell_scale, g_quantile,
+        w.params, w.ticket, w.partial);
     FFB6D_LAUNCH_OK("grid_prepare_kernel");
+    dim3 tgrid((unsigned)w.ntiles, (unsigned)B);
+    grid_zero_kernel<<<tgrid, 256, 0, st>>>(w.params, w.cursor, w.maxc, w.tile_sum, (int)w.ntiles);
+    FFB6D_LAUNCH_OK("grid_zero_kernel");
     dim3 pgrid((unsigned)ceil_div(S, 256), (unsigned)B);
-    grid_count_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, stride, w.tile_sum,
+    grid_count_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, w.maxc, w.tile_sum,
                                              (int)w.ntiles);
     FFB6D_LAUNCH_OK("grid_count_kernel");
-    grid_scan_kernel<<<dim3((unsigned)w.ntiles, (unsigned)B), 1024, 0, st>>>(w.params, w.cursor, stride,
-                                                                             w.tile_sum, (int)w.ntiles);
+    grid_scan_kernel<<<tgrid, 1024, 0, st>>>(w.params, w.cursor, w.maxc, w.tile_sum, (int)w.ntiles);
     FFB6D_LAUNCH_OK("grid_scan_kernel");
-    grid_scatter_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, stride, w.sorted);
+    grid_scatter_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, w.maxc, w.sorted);
     FFB6D_LAUNCH_OK("grid_scatter_kernel");
-    if (idx_is_i64) return launch_search_k<long long>(support, query, B, S, Q, K, idx_out, w, st);
-    return launch_search_k<int>(support, query, B, S, Q, K, idx_out, w, st);
+    return FFB6D_OK;
+}
+
+// Search a built grid.  `support` must be the array the grid was built from.
+int knn_grid_query(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
+                   void *idx_out, int idx_is_i64, const void *grid_mem, size_t grid_bytes,
+                   void *scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    read_env();
+    GridStore w = carve_grid(const_cast<void *>(grid_mem), B, S);
+    QueryScratch qs = carve_query(scratch, B, Q);
+    if (!grid_mem || grid_bytes < w.bytes || !scratch || scratch_bytes < qs.bytes) {
+        set_error("knn grid query: storage too small (grid %zu/%zu, scratch %zu/%zu)", grid_bytes, w.bytes,
+                  scratch_bytes, qs.bytes);
+        return FFB6D_ERR_WORKSPACE;
+    }
+    if (idx_is_i64) return launch_search_k<long long>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    return launch_search_k<int>(support, query, B, S, Q, K, idx_out, w, qs, st);
+}
+
+int knn_grid_launch(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
+                    void *idx_out, int idx_is_i64, void *workspace, size_t workspace_bytes,
+                    cudaStream_t st)
+{
+    const size_t gb = knn_grid_store_bytes(B, S), qb = knn_grid_query_bytes(B, Q);
+    if (!workspace || workspace_bytes < gb + qb) {
+        set_error("knn grid: workspace too small (%zu < %zu)", workspace_bytes, gb + qb);
+        return FFB6D_ERR_WORKSPACE;
+    }
+    int rc = knn_grid_build(support, B, S, K, workspace, gb, st);
+    if (rc) return rc;
+    return knn_grid_query(support, query, B, S, Q, K, idx_out, idx_is_i64, workspace, gb,
+                          (char *)workspace + gb, qb, st);
 }
 
 }  // namespace ffb6d

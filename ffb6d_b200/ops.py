@@ -93,6 +93,60 @@ def knn_search(support_pts, query_pts, k, out_dtype=None, algo=0):
     return out
 
 
+class KnnGrid:
+    """Uniform-grid index of a support batch: build once, search many times
+    (``ffb6d_knn_grid_build`` / ``ffb6d_knn_grid_query``).  The FFB6D schedule searches every
+    pyramid level two to four times (datasets/ycb/ycb_dataset.py:275-308); sharing the grid
+    removes the repeated builds.  Results are identical to :func:`knn_search`.
+
+    :param support: ``[B, S, 3]`` float32 CUDA tensor
+    :param k_hint: the neighbour count the grid will mostly be searched with (tunes the cell
+      size only; any ``k`` may be queried)
+    """
+
+    def __init__(self, support, k_hint):
+        _need_cuda(support, "support")
+        sup = support.contiguous().float()
+        if sup.dim() != 3 or sup.shape[2] != 3 or sup.shape[1] < 1:
+            raise ValueError("KnnGrid expects a non-empty [B,S,3] support, got %s" % (tuple(sup.shape),))
+        self.support = sup
+        self.B, self.S = sup.shape[0], sup.shape[1]
+        self.k_hint = int(k_hint)
+        with torch.cuda.device(sup.device):
+            self.nbytes = int(lib.ffb6d_knn_grid_bytes(self.B, self.S))
+            self.mem = torch.empty(self.nbytes, dtype=torch.uint8, device=sup.device)
+            check(lib.ffb6d_knn_grid_build(sup.data_ptr(), self.B, self.S, self.k_hint,
+                                           self.mem.data_ptr(), self.nbytes, _stream(sup.device)))
+
+    def query(self, query_pts, k, out_dtype=None):
+        """``query_pts [B,Q,3]`` -> ``[B,Q,k]`` neighbour indices into the support (int32 unless
+        ``out_dtype`` is torch.int64).  Pass the support tensor itself for a self search."""
+        _need_cuda(query_pts, "query_pts")
+        qry = self.support if query_pts is self.support else query_pts.contiguous().float()
+        if qry.dim() != 3 or qry.shape[0] != self.B or qry.shape[2] != 3:
+            raise ValueError("query must be [B,Q,3] with B=%d, got %s" % (self.B, tuple(qry.shape)))
+        k = int(k)
+        Q = qry.shape[1]
+        dt = torch.int32 if out_dtype is None else out_dtype
+        if dt not in _IDX:
+            raise TypeError("out_dtype must be torch.int32 or torch.int64")
+        dev = self.support.device
+        out = torch.empty((self.B, Q, k), dtype=dt, device=dev)
+        with torch.cuda.device(dev):
+            sb = int(lib.ffb6d_knn_grid_query_bytes(self.B, Q))
+            scratch = torch.empty(max(sb, 1), dtype=torch.uint8, device=dev)
+            check(lib.ffb6d_knn_grid_query(self.support.data_ptr(), qry.data_ptr(), self.B, self.S, Q, k,
+                                           out.data_ptr(), int(dt == torch.int64), self.mem.data_ptr(),
+                                           self.nbytes, scratch.data_ptr(), sb, _stream(dev)))
+        return out
+
+
+def knn_uses_grid(B, S, Q, k):
+    """True when :func:`knn_search` would answer this problem with the grid search (rather than
+    the tiled scan it uses for small problems)."""
+    return int(lib.ffb6d_knn_workspace_bytes(B, S, Q, int(k))) > 0
+
+
 # --------------------------------------------------------------------------- gather + max
 def _layout_of(f3):
     """f3: [B,C,S] view.  Returns (tensor, layout) with tensor dense in that layout."""

@@ -7,9 +7,11 @@ gather (models/ffb6d.py:231-312).  This module states both schedules as data and
 runs the index build on the GPU for a whole batch: xyz goes in, the same dict
 keys with the same shapes and dtypes (int32) come out, already on the device.
 """
+import contextlib
+
 import torch
 
-from .ops import knn_search
+from .ops import knn_search, KnnGrid, knn_uses_grid
 
 # reference literals (ycb_dataset.py:269-271, 298)
 RGB_DS_SR = (4, 8, 8, 8)
@@ -146,26 +148,53 @@ def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=
             n //= PCLD_SUB_S_R[i]
     inputs = {}
     calls = knn_schedule(n0, H, W, k)
-    if streams is None or timer is not None:
-        for key, s, q, kk in calls:
-            sup, qry = sets[s], sets[q]
+    # one grid per (point set, K class) shared by all the searches into it; supports whose
+    # searches are all tiny keep the tiled scan
+    groups = {}
+    for key, s, q, kk in calls:
+        groups.setdefault((s, kk), []).append((key, q))
+    gridded = [g for g, members in groups.items()
+               if any(knn_uses_grid(B, sets[g[0]].shape[1], sets[q].shape[1], g[1]) for _, q in members)]
+    grids = {}
+    main = torch.cuda.current_stream(cld.device)
+    par = streams is not None and timer is None
+
+    def fork():
+        if par:
+            for st in streams:
+                st.wait_stream(main)
+
+    def join():
+        if par:
+            for st in streams:
+                main.wait_stream(st)
+
+    def on(i):
+        return torch.cuda.stream(streams[i % len(streams)]) if par else contextlib.nullcontext()
+
+    fork()
+    for i, g in enumerate(sorted(gridded, key=lambda g: -sets[g[0]].shape[1])):
+        with on(i):
             if timer is not None:
-                timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
-            inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype)
+                timer.start("knn_build:%s%d:k%d" % (g[0][0], g[0][1], g[1]), 0)
+            grids[g] = KnnGrid(sets[g[0]], g[1])
             if timer is not None:
                 timer.stop()
-    else:
-        # the 22 searches are independent: spread them over side streams (biggest first) so the
-        # many small launches overlap instead of queueing behind each other
-        main = torch.cuda.current_stream(cld.device)
-        order = sorted(calls, key=lambda c: -(sets[c[1]].shape[1] + sets[c[2]].shape[1] * c[3]))
-        for st in streams:
-            st.wait_stream(main)
-        for i, (key, s, q, kk) in enumerate(order):
-            with torch.cuda.stream(streams[i % len(streams)]):
-                inputs[key] = knn_search(sets[s], sets[q], kk, out_dtype=index_dtype)
-        for st in streams:
-            main.wait_stream(st)
+    join()
+    fork()
+    order = sorted(calls, key=lambda c: -(sets[c[2]].shape[1] * c[3])) if par else calls
+    for i, (key, s, q, kk) in enumerate(order):
+        sup, qry = sets[s], sets[q]
+        with on(i):
+            if timer is not None:
+                timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
+            if (s, kk) in grids:
+                inputs[key] = grids[(s, kk)].query(qry, kk, out_dtype=index_dtype)
+            else:
+                inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype, algo=1)
+            if timer is not None:
+                timer.stop()
+    join()
     for i in range(N_DS_LAYERS):
         inputs["cld_xyz%d" % i] = sets[("cld", i)]
         n_sub = sets[("cld", i + 1)].shape[1]

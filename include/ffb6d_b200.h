@@ -92,6 +92,26 @@ int ffb6d_knn_batch_algo(const float *support, const float *query,
                          void *workspace, size_t workspace_bytes,
                          int algo, ffb6d_stream_t stream);
 
+/*
+ * Build-once / query-many form of the same search, for callers that search one support
+ * cloud several times (the FFB6D schedule searches each pyramid level 2-4 times,
+ * datasets/ycb/ycb_dataset.py:275-308).  The grid (uniform-cell index of `support`) is
+ * written by ffb6d_knn_grid_build into caller memory of ffb6d_knn_grid_bytes(B,S) bytes and
+ * is read-only afterwards: queries may run concurrently on any streams ordered after the
+ * build.  K_hint only tunes the cell size (performance); results never depend on it.  Each
+ * query call needs its own scratch of ffb6d_knn_grid_query_bytes(B,Q) bytes.  `support`
+ * must be the array the grid was built from.  Results are identical to ffb6d_knn_batch.
+ */
+size_t ffb6d_knn_grid_bytes(int64_t B, int64_t S);
+size_t ffb6d_knn_grid_query_bytes(int64_t B, int64_t Q);
+int ffb6d_knn_grid_build(const float *support, int64_t B, int64_t S, int K_hint,
+                         void *grid, size_t grid_bytes, ffb6d_stream_t stream);
+int ffb6d_knn_grid_query(const float *support, const float *query,
+                         int64_t B, int64_t S, int64_t Q, int K,
+                         void *idx_out, int idx_is_i64,
+                         const void *grid, size_t grid_bytes,
+                         void *scratch, size_t scratch_bytes, ffb6d_stream_t stream);
+
 /* HOST-pointer twins with the reference's exact signatures (NN/knn_.h:2-16);
  * dim must be 3.  `long` is int64 on LP64, as in the reference. */
 int ffb6d_knn_batch_host(const float *batch_data, size_t batch_size, size_t npts, size_t dim,

@@ -159,3 +159,20 @@ def test_schedule_properties_at_full_batch(cuda):
     solo = F.build_ffb6d_indices(cld[:1], xyz[:1])
     for key in solo:
         assert torch.equal(solo[key][0], inputs[key][0]), key
+
+
+def test_knn_grid_build_once_query_many(cuda):
+    """KnnGrid: one grid, several searches with different K and query sets == knn_search."""
+    rs = np.random.RandomState(12)
+    sup = rs.rand(2, 5000, 3).astype(np.float32) * np.array([1.0, 0.8, 0.2], np.float32)
+    q1 = rs.rand(2, 700, 3).astype(np.float32)
+    q2 = (rs.rand(2, 50, 3).astype(np.float32) - 3.0)          # far outside -> overflow path
+    q2[:, 10:30] = 0.0                                          # equal far queries (+0.0 / -0.0)
+    q2[:, 20:30, 0] = -0.0
+    ts = torch.from_numpy(sup).cuda()
+    grid = F.KnnGrid(ts, 16)
+    for q, k in ((q1, 16), (q1, 1), (q2, 16), (q2, 1), (q1, 7), (q1, 33)):
+        got = grid.query(torch.from_numpy(q).cuda(), k).cpu().numpy()
+        assert np.array_equal(got, O.knn_search(sup, q, k)), (q.shape, k)
+    got = grid.query(ts, 16, out_dtype=torch.int64).cpu().numpy()              # self search
+    assert np.array_equal(got, O.knn_search(sup, sup, 16))

@@ -19,7 +19,7 @@ dev = torch.device("cuda:0")
 cld = torch.from_numpy(batch["cld"]).to(dev)
 xyz = torch.from_numpy(batch["dpt_xyz"]).to(dev)
 cho = torch.from_numpy(batch["choose"]).to(dev)
-p = FusionPass(B, device=dev, layout=layout)
+p = FusionPass(B, device=dev, layout=layout, n_streams=int(os.environ.get("NSTREAMS", "1")))
 for _ in range(3):
     p(cld, xyz, cho)
 torch.cuda.synchronize()
