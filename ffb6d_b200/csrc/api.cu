@@ -165,6 +165,8 @@ int ffb6d_knn_grid_query(const float *support, const float *query, int64_t B, in
                           scratch_bytes, (cudaStream_t)stream);
 }
 
+void ffb6d_knn_grid_tune(float cell_scale, int quantile) { knn_grid_tune(cell_scale, quantile); }
+
 int ffb6d_knn_batch_host(const float *batch_data, size_t batch_size, size_t npts, size_t dim,
                          const float *queries, size_t nqueries, size_t K, long *batch_indices)
 {

@@ -21,6 +21,7 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <stdlib.h>
 
 namespace ffb6d {
 
@@ -138,21 +139,31 @@ gather1_ncs_staged_v4_kernel(const float *__restrict__ feat, const IdxT *__restr
     const int q1 = min(Q, q0 + q_per_cta);          // Q is a multiple of 4
     float *dst = out + ((size_t)b * C + c0) * Q;
     const IdxT *ib = idx + (size_t)b * Q;
-    for (int q = q0 + threadIdx.x * 4; q < q1; q += blockDim.x * 4) {
-        int i0, i1, i2, i3;
+    auto load4 = [&](int q, int (&id)[4]) {
         if constexpr (sizeof(IdxT) == 4) {
             const int4 v = __ldg(reinterpret_cast<const int4 *>(ib + q));
-            i0 = v.x; i1 = v.y; i2 = v.z; i3 = v.w;
+            id[0] = v.x; id[1] = v.y; id[2] = v.z; id[3] = v.w;
         } else {
             const longlong2 u = __ldg(reinterpret_cast<const longlong2 *>(ib + q));
             const longlong2 w = __ldg(reinterpret_cast<const longlong2 *>(ib + q) + 1);
-            i0 = (int)u.x; i1 = (int)u.y; i2 = (int)w.x; i3 = (int)w.y;
+            id[0] = (int)u.x; id[1] = (int)u.y; id[2] = (int)w.x; id[3] = (int)w.y;
         }
+    };
+    // two index loads in flight per thread; the loop is otherwise bound by the latency of that load
+    const int step = blockDim.x * 4;
+    for (int q = q0 + threadIdx.x * 4; q < q1; q += 2 * step) {
+        int ia[4], ibb[4] = {0, 0, 0, 0};
+        const bool two = q + step < q1;
+        load4(q, ia);
+        if (two) load4(q + step, ibb);
 #pragma unroll 4
         for (int c = 0; c < cc; ++c) {
             const float *r = rows + c * S;
-            const float4 v = make_float4(r[i0], r[i1], r[i2], r[i3]);
-            __stcs(reinterpret_cast<float4 *>(dst + (size_t)c * Q + q), v);   // streaming store
+            __stcs(reinterpret_cast<float4 *>(dst + (size_t)c * Q + q),
+                   make_float4(r[ia[0]], r[ia[1]], r[ia[2]], r[ia[3]]));
+            if (two)
+                __stcs(reinterpret_cast<float4 *>(dst + (size_t)c * Q + q + step),
+                       make_float4(r[ibb[0]], r[ibb[1]], r[ibb[2]], r[ibb[3]]));
         }
     }
 }
@@ -210,6 +221,60 @@ gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restr
             dst[(size_t)c * Q + q] = m;
         }
     }
+}
+
+// Rows longer than shared memory with K > 1 (r2p gathers from the 240x320 map): the row is
+// streamed through shared memory in pieces; every piece updates a running maximum per query
+// (also in shared memory) with the neighbours that fall inside it.  Turns Q*K scattered
+// L1/L2 reads per row into one coalesced read of the row plus shared-memory gathers.
+template <typename IdxT, int KT>
+__global__ void __launch_bounds__(256)
+gather_max_ncs_split_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                            float *__restrict__ out, int C, int S, int Q, int K, int piece,
+                            int q_per_cta)
+{
+    extern __shared__ __align__(16) float sm[];
+    float *rowp = sm;            // [piece]
+    float *mx = sm + piece;      // [q_per_cta]
+    const int b = blockIdx.z, c = blockIdx.y;
+    const int q0 = blockIdx.x * q_per_cta;
+    const int nq = min(q_per_cta, Q - q0);
+    const float *src = feat + ((size_t)b * C + c) * S;
+    const IdxT *ib = idx + ((size_t)b * Q + q0) * K;
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) mx[i] = __int_as_float(0xff800000);   // -inf
+    const bool vec = ((S & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
+    for (int p0 = 0; p0 < S; p0 += piece) {
+        const int n = min(piece, S - p0);
+        __syncthreads();
+        if (vec) {   // piece and p0 are multiples of 4
+            const float4 *s4 = reinterpret_cast<const float4 *>(src + p0);
+            float4 *d4 = reinterpret_cast<float4 *>(rowp);
+            for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
+        } else {
+            for (int t = threadIdx.x; t < n; t += blockDim.x) rowp[t] = __ldg(src + p0 + t);
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
+            float m = mx[i];
+            if constexpr (KT > 0) {
+                int id[KT];
+                load_ids<IdxT, KT>(ib + (size_t)i * K, K, id);
+#pragma unroll
+                for (int k = 0; k < KT; ++k) {
+                    const unsigned off = (unsigned)(id[k] - p0);
+                    if (off < (unsigned)n) m = max_nan(m, rowp[off]);
+                }
+            } else {
+                for (int k = 0; k < K; ++k) {
+                    const unsigned off = (unsigned)((int)__ldg(ib + (size_t)i * K + k) - p0);
+                    if (off < (unsigned)n) m = max_nan(m, rowp[off]);
+                }
+            }
+            mx[i] = m;   // slot i is only ever touched by this thread
+        }
+    }
+    float *dst = out + ((size_t)b * C + c) * Q + q0;
+    for (int i = threadIdx.x; i < nq; i += blockDim.x) dst[i] = mx[i];
 }
 
 // K == 1 with long rows (the `choose` gather): eight channels per thread, loads first
@@ -429,7 +494,8 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         // is large (index bytes ~ K/CC of the output bytes), narrow when K == 1
         const int cc_cap = (KT == 1) ? 8 : 32;
         if (CC > cc_cap) CC = cc_cap;
-        while (CC > 1 && B * ceil_div(C, CC) < want && (KT == 1 || CC > 4)) CC = (CC + 1) / 2;
+        if (KT != 1)
+            while (CC > 4 && B * ceil_div(C, CC) < want) CC = (CC + 1) / 2;
         const int64_t ctas = B * ceil_div(C, CC);
         int64_t nq = ctas < want ? ceil_div(want, ctas) : 1;
         // every query chunk stages the rows again: keep a chunk at least 4 rows long
@@ -470,6 +536,23 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, 8), (unsigned)B);
         gather1_ncs_direct_kernel<IdxT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
         FFB6D_LAUNCH_OK("gather1_ncs_direct_kernel");
+    } else if (C <= 65535 && !getenv("FFB6D_GATHER_DIRECT")) {
+        const int q_per_cta = (int)std::min<int64_t>(Q, 4096);
+        int piece = (int)((budget - (size_t)q_per_cta * sizeof(float)) / sizeof(float));
+        piece = piece / 1024 * 1024;
+        const int pieces = (int)ceil_div(S, piece);
+        piece = (int)(ceil_div(ceil_div(S, pieces), 1024) * 1024);   // even pieces
+        const size_t smem = ((size_t)piece + q_per_cta) * sizeof(float);
+        auto kern = gather_max_ncs_split_kernel<IdxT, KT>;
+        static bool optin_done = false;
+        if (!optin_done) {
+            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            max_smem_optin()));
+            optin_done = true;
+        }
+        dim3 grid((unsigned)ceil_div(Q, q_per_cta), (unsigned)C, (unsigned)B);
+        kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, piece, q_per_cta);
+        FFB6D_LAUNCH_OK("gather_max_ncs_split_kernel");
     } else {
         const int CC = 8;
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, CC), (unsigned)B);

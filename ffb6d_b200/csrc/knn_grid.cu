@@ -453,6 +453,20 @@ grid_scatter_kernel(const float *__restrict__ support, int S, const GridParams *
     // after this kernel cursor[c] is the END of cell c; its start is cursor[c-1] (0 for c == 0)
 }
 
+// (dz, dy) offsets of the cell rows of a block, nearest first: nested by Chebyshev ring (entries
+// [0,9) ring <= 1, [0,25) ring <= 2, [0,49) ring <= 3, [0,81) ring <= 4), Euclid-sorted inside a ring.
+// Scanning rows centre-out makes the K-th distance tight early, so later rows are mostly pruned
+// by their minimum possible distance.
+__constant__ signed char kRowOrder[81][2] = {{0,0}, {-1,0}, {0,-1}, {0,1}, {1,0}, {-1,-1}, {-1,1}, {1,-1}, {1,1}, {-2,0}, {0,-2}, {0,2}, {2,0}, {-2,-1}, {-2,1}, {-1,-2}, {-1,2}, {1,-2}, {1,2}, {2,-1}, {2,1}, {-2,-2}, {-2,2}, {2,-2}, {2,2}, {-3,0}, {0,-3}, {0,3}, {3,0}, {-3,-1}, {-3,1}, {-1,-3}, {-1,3}, {1,-3}, {1,3}, {3,-1}, {3,1}, {-3,-2}, {-3,2}, {-2,-3}, {-2,3}, {2,-3}, {2,3}, {3,-2}, {3,2}, {-3,-3}, {-3,3}, {3,-3}, {3,3}, {-4,0}, {0,-4}, {0,4}, {4,0}, {-4,-1}, {-4,1}, {-1,-4}, {-1,4}, {1,-4}, {1,4}, {4,-1}, {4,1}, {-4,-2}, {-4,2}, {-2,-4}, {-2,4}, {2,-4}, {2,4}, {4,-2}, {4,2}, {-4,-3}, {-4,3}, {-3,-4}, {-3,4}, {3,-4}, {3,4}, {4,-3}, {4,3}, {-4,-4}, {-4,4}, {4,-4}, {4,4}};
+
+// squared distance from coordinate q to the slab [lo + c*h, lo + (c+1)*h], shrunk by the safety slack
+__device__ __forceinline__ float slab_dist2(float q, float lo, float h, int c, float slack)
+{
+    const float a = lo + (float)c * h, b = lo + (float)(c + 1) * h;
+    const float d = fmaxf(fmaxf(a - q, q - b) - slack, 0.f);
+    return d * d;
+}
+
 // ------------------------------------------------------------------ E. search
 template <int KCAP, typename IdxT, bool SELF>
 __global__ void __launch_bounds__(128)
@@ -518,16 +532,25 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
         const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
         const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
-        for (int z = z0; z <= z1; ++z) {
-            for (int y = y0; y <= y1; ++y) {
+        const int e0 = (2 * r - 1) * (2 * r - 1) * (r > r_first ? 1 : 0);   // rows of the inner block are done
+        const int e1 = (2 * r + 1) * (2 * r + 1);
+        // new x-cells of the rows already visited (ring growth)
+        if (r > r_first) {
+            for (int e = 0; e < e0; ++e) {
+                const int z = cz + kRowOrder[e][0], y = cy + kRowOrder[e][1];
+                if (z < pz0 || z > pz1 || y < py0 || y > py1) continue;
                 const int row = (z * ny + y) * nx;
-                if (z >= pz0 && z <= pz1 && y >= py0 && y <= py1) {   // row seen before: only its new ends
-                    if (x0 < px0) cells(row, x0, px0 - 1);
-                    if (x1 > px1) cells(row, px1 + 1, x1);
-                } else {
-                    cells(row, x0, x1);
-                }
+                if (x0 < px0) cells(row, x0, px0 - 1);
+                if (x1 > px1) cells(row, px1 + 1, x1);
             }
+        }
+        for (int e = e0; e < e1; ++e) {   // centre-out
+            const int z = cz + kRowOrder[e][0], y = cy + kRowOrder[e][1];
+            if (z < z0 || z > z1 || y < y0 || y > y1) continue;
+            // skip rows that cannot hold anything closer than the current K-th best
+            const float dmin2 = slab_dist2(qy, Ps.lo[1], h, y, slack) + slab_dist2(qz, Ps.lo[2], h, z, slack);
+            if (dmin2 > top.kth(K)) continue;
+            cells((z * ny + y) * nx, x0, x1);
         }
         px0 = x0; px1 = x1; py0 = y0; py1 = y1; pz0 = z0; pz1 = z1;
         // distance from the query to the nearest face of the block that still has cells behind it
@@ -671,15 +694,26 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
         const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
         const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
-        const int nyb = y1 - y0 + 1;
-        const int nrows = nyb * (z1 - z0 + 1);
-        for (int row0 = 0; row0 < nrows; row0 += 32) {
-            const int rr = row0 + lane;
+        const int e_end = (2 * r + 1) * (2 * r + 1);
+        // row groups, centre-out: {centre + 4 adjacent}, {4 diagonal}, ring 2, ring 3, ring 4
+        for (int g = 0; g < 5; ++g) {
+            const int gs = (g == 0) ? 0 : (g == 1) ? 5 : (g == 2) ? 9 : (g == 3) ? 25 : 49;
+            const int ge = (g == 0) ? 5 : (g == 1) ? 9 : (g == 2) ? 25 : (g == 3) ? 49 : 81;
+            if (gs >= e_end) break;
+            const float kth_now = __shfl_sync(FULL, my_d, K - 1);   // +inf until K candidates were seen
+            const int e = gs + lane;
             int beg = 0, end = 0;
-            if (rr < nrows) {
-                const int row = ((z0 + rr / nyb) * ny + (y0 + rr % nyb)) * nx;
-                beg = (row + x0 > 0) ? __ldg(cell_end + row + x0 - 1) : 0;
-                end = __ldg(cell_end + row + x1);
+            if (e < ge) {
+                const int z = cz + kRowOrder[e][0], y = cy + kRowOrder[e][1];
+                if (z >= z0 && z <= z1 && y >= y0 && y <= y1) {
+                    // rows that cannot hold anything closer than the current K-th best are skipped
+                    const float dmin2 = slab_dist2(qy, Ps.lo[1], h, y, slack) + slab_dist2(qz, Ps.lo[2], h, z, slack);
+                    if (!(dmin2 > kth_now)) {
+                        const int row = (z * ny + y) * nx;
+                        beg = (row + x0 > 0) ? __ldg(cell_end + row + x0 - 1) : 0;
+                        end = __ldg(cell_end + row + x1);
+                    }
+                }
             }
             const int cnt = end - beg;
             int incl = cnt;
@@ -939,6 +973,13 @@ static void read_env()
     if (const char *e = getenv("FFB6D_GRID_THREAD_SEARCH")) g_force_thread_search = atoi(e) != 0;
     if (const char *e = getenv("FFB6D_GRID_QUANTILE")) g_quantile = std::min(31, std::max(0, atoi(e)));
     g_env_read = true;
+}
+
+void knn_grid_tune(float cell_scale, int quantile)
+{
+    read_env();
+    if (cell_scale > 0.f) g_cell_scale = cell_scale;
+    if (quantile >= 0) g_quantile = std::min(31, quantile);
 }
 
 template <int KCAP, typename IdxT>

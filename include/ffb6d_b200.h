@@ -112,6 +112,11 @@ int ffb6d_knn_grid_query(const float *support, const float *query,
                          const void *grid, size_t grid_bytes,
                          void *scratch, size_t scratch_bytes, ffb6d_stream_t stream);
 
+/* Performance knobs of the grid search (never affect results): the cell edge is
+ * cell_scale x the `quantile`-th smallest (0..31) of 32 sampled K-th-neighbour distances.
+ * Non-positive / negative arguments leave a knob unchanged.  Defaults 1.0 and 17. */
+void ffb6d_knn_grid_tune(float cell_scale, int quantile);
+
 /* HOST-pointer twins with the reference's exact signatures (NN/knn_.h:2-16);
  * dim must be 3.  `long` is int64 on LP64, as in the reference. */
 int ffb6d_knn_batch_host(const float *batch_data, size_t batch_size, size_t npts, size_t dim,
