@@ -223,13 +223,17 @@ def load_ncu_traffic():
 
 
 def kernel_family(op_name):
-    """Map a timed op to the kernel function that runs it."""
-    kind, key = op_name.split(":", 1)
+    """Map a timed op to the kernel (family) that runs it.  Gathers are single kernels and are
+    grouped by kernel function; a KNN search op is grid_search_* + overflow + dup-copy (the search
+    kernel is > 90 % of it), a KNN build op is the five grid-build kernels."""
+    parts = op_name.split(":")
+    kind, key = parts[0], parts[1]
+    if kind == "gather":
+        return parts[2]
     if kind == "knn_build":
-        return "knn_k1" if key.endswith(":k1") else "knn_k16"
-    if kind == "knn":
-        return "knn_k1" if ("interp" in key or key.startswith("p2r")) else "knn_k16"
-    return "gather_k1" if (key.startswith("p2r") or "interp" in key or key == "choose") else "gather_max_k16"
+        return "grid build (prepare+zero+count+scan+scatter)"
+    k1 = "interp" in key or key.startswith("p2r")
+    return "grid_search_kernel<K=1> (+knn_brute for S<512)" if k1 else "grid_search_warp_kernel<K=16>"
 
 
 def main():
@@ -407,10 +411,11 @@ def main():
     dom = max(fam, key=lambda k: fam[k]["ms"])
     dd = fam[dom]
     achieved = dd["bytes"] / (dd["ms"] / 1e3) / 1e9
-    traffic = load_ncu_traffic().get(dom)
+    cap = load_ncu_traffic().get(dom, {}) if isinstance(load_ncu_traffic().get(dom), dict) else {}
+    traffic = cap.get("traffic_bytes")
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+        "frac": achieved / peak, "traffic": traffic, "traffic_capture": cap or None, "peak_source": peak_src,
         "share_of_step": dd["ms"] / tot_ms, "ops_per_step": dd["n"] // steps,
         "alg_bytes_per_launch": dd["bytes"] / dd["n"], "avg_launch_ms": dd["ms"] / dd["n"],
         "families": {k: {"share": v["ms"] / tot_ms, "ms_per_step": v["ms"] / steps,

@@ -277,6 +277,53 @@ gather_max_ncs_split_kernel(const float *__restrict__ feat, const IdxT *__restri
     for (int i = threadIdx.x; i < nq; i += blockDim.x) dst[i] = mx[i];
 }
 
+// Long rows with K = 8/16/32 (r2p gathers from the 240x320 map): the K lanes of a group hold the K
+// neighbours of ONE query.  Neighbours of a query are adjacent pixels, so a warp-wide load touches
+// a handful of 32-byte sectors instead of 32 (lanes along the query axis would scatter every
+// lane into its own sector); the max over the group is a log2(K)-step shuffle reduction.  Results
+// are collected in a [channel][query] shared-memory tile and written out coalesced.
+template <typename IdxT, int KT>
+__global__ void __launch_bounds__(256)
+gather_max_ncs_klane_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
+                            float *__restrict__ out, int C, int S, int Q)
+{
+    constexpr int TQ = 32;            // queries per CTA tile (one 128-byte output segment per channel)
+    constexpr int QPW = 32 / KT;      // queries per warp at a time
+    constexpr int CCH = 64;           // channels per CTA pass
+    __shared__ float tile[CCH][TQ + 1];
+    const int b = blockIdx.z;
+    const int q_tile = blockIdx.x * TQ;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int grp = lane / KT, kl = lane % KT;
+    const float *fb = feat + (size_t)b * C * S;
+    for (int c0 = blockIdx.y * CCH; c0 < C; c0 += gridDim.y * CCH) {
+        const int cc = min(CCH, C - c0);
+        for (int ql = wid * QPW + grp; ql < TQ; ql += 8 * QPW) {
+            const int q = q_tile + ql;
+            const bool on = q < Q;
+            const int id = on ? (int)__ldg(idx + ((size_t)b * Q + q) * KT + kl) : 0;
+            const float *src = fb + (size_t)c0 * S + id;
+            for (int c = 0; c < cc; c += 4) {   // four independent loads in flight
+                float v[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) v[u] = (c + u < cc) ? __ldg(src + (size_t)(c + u) * S) : 0.f;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+#pragma unroll
+                    for (int o = KT / 2; o > 0; o >>= 1) v[u] = max_nan(v[u], __shfl_xor_sync(0xffffffffu, v[u], o));
+                    if (kl == 0 && c + u < cc) tile[c + u][ql] = v[u];
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = threadIdx.x; t < cc * TQ; t += blockDim.x) {
+            const int c = t / TQ, ql = t % TQ;
+            if (q_tile + ql < Q) out[((size_t)b * C + c0 + c) * Q + q_tile + ql] = tile[c][ql];
+        }
+        __syncthreads();
+    }
+}
+
 // K == 1 with long rows (the `choose` gather): eight channels per thread, loads first
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
@@ -536,7 +583,13 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, 8), (unsigned)B);
         gather1_ncs_direct_kernel<IdxT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
         FFB6D_LAUNCH_OK("gather1_ncs_direct_kernel");
-    } else if (C <= 65535 && !getenv("FFB6D_GATHER_DIRECT")) {
+    } else if ((KT == 8 || KT == 16 || KT == 32) && !getenv("FFB6D_GATHER_DIRECT")) {
+        if constexpr (KT == 8 || KT == 16 || KT == 32) {
+            dim3 grid((unsigned)ceil_div(Q, 32), (unsigned)std::min<int64_t>(ceil_div(C, 64), 65535), (unsigned)B);
+            gather_max_ncs_klane_kernel<IdxT, KT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
+            FFB6D_LAUNCH_OK("gather_max_ncs_klane_kernel");
+        }
+    } else if (C <= 65535 && getenv("FFB6D_GATHER_SPLIT")) {   // measured slower than the direct kernel on B200: opt-in
         const int q_per_cta = (int)std::min<int64_t>(Q, 4096);
         int piece = (int)((budget - (size_t)q_per_cta * sizeof(float)) / sizeof(float));
         piece = piece / 1024 * 1024;
@@ -588,6 +641,21 @@ static int gather_max_fwd_t(const float *feat, const IdxT *idx, int64_t B, int64
 using namespace ffb6d;
 
 extern "C" {
+
+const char *ffb6d_gather_kernel_name(int64_t B, int64_t C, int64_t S, int64_t Q, int K, int layout)
+{
+    // mirrors gather_max_fwd_t / launch_ncs (aligned pointers assumed)
+    (void)B;
+    (void)C;
+    if (layout == FFB6D_LAYOUT_NSC) return "gather_max_nsc_kernel";
+    const size_t budget = (size_t)(max_smem_optin() - 1024) / 2;
+    const bool fits = (size_t)S * sizeof(float) <= budget;
+    if (K == 1) return fits ? ((Q % 4 == 0) ? "gather1_ncs_staged_v4_kernel" : "gather_max_ncs_staged_kernel")
+                            : "gather1_ncs_direct_kernel";
+    if (fits) return "gather_max_ncs_staged_kernel";
+    if ((K == 8 || K == 16 || K == 32) && !getenv("FFB6D_GATHER_DIRECT")) return "gather_max_ncs_klane_kernel";
+    return "gather_max_ncs_direct_kernel";
+}
 
 int ffb6d_gather_max_fwd(const float *feat, const void *idx, int idx_is_i64, int64_t B, int64_t C,
                          int64_t S, int64_t Q, int K, int layout, float *out,

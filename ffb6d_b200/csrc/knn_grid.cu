@@ -597,38 +597,76 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
 }
 
 // ------------------------------------------------------------------ E'. search, one WARP per query
-// For 2 <= K <= 32.  The sorted top list lives across the lanes (lane j holds the j-th best
-// (distance, index)); the cell rows of the block are looked up by the lanes in parallel, their
-// point ranges are flattened with a warp prefix sum so every batch of 32 candidates keeps all
-// lanes busy (one coalesced 512-byte read), and candidates enter the list either one by one
-// (shift-insert through shuffles) or, when many qualify, by a bitonic sort + merge.  Compared
-// with one thread per query this removes the divergence between neighbouring queries and gives
-// the small searches of the schedule (48 ... 3072 queries per frame) 32x more parallelism.
-__device__ __forceinline__ bool pair_less(float ad, int ai, float bd, int bi)
+// For 2 <= K <= 32.  The sorted top list lives across the lanes (lane j holds the j-th best) as
+// one 64-bit key per entry, (distance bits << 32) | index: squared distances are non-negative so
+// their bit patterns order like unsigned integers and ONE unsigned compare implements the total
+// order (distance, index).  The cell rows of the block are looked up by the lanes in parallel
+// (centre-out, rows that cannot beat the current K-th distance are skipped), their point ranges
+// are flattened with a warp prefix sum so every batch of 32 candidates keeps all lanes busy (one
+// coalesced 512-byte read), and candidates enter the list either one by one (shift-insert through
+// shuffles) or, when many qualify, by a bitonic sort + merge.  When the block has to grow, only
+// the new shell is scanned (new rows, and the new end cells of the old rows) and the list is
+// kept.  Compared with one thread per query this removes the divergence between neighbouring
+// queries and gives the small searches of the schedule (48 ... 3072 queries per frame) 32x more
+// parallelism.
+typedef unsigned long long key_t64;
+
+__device__ __forceinline__ key_t64 make_key(float d, int i)
 {
-    return ad < bd || (ad == bd && ai < bi);
+    return ((key_t64)__float_as_uint(d) << 32) | (unsigned)i;
+}
+__device__ __forceinline__ float key_dist(key_t64 k) { return __uint_as_float((unsigned)(k >> 32)); }
+
+constexpr key_t64 KEY_EMPTY = 0x7f80000000000000ull;     // (+inf, index 0): what an unfilled slot reports
+constexpr key_t64 KEY_INVALID = 0x7f8000007fffffffull;   // (+inf, INT_MAX): a lane without a candidate
+
+__device__ __forceinline__ void warp_minmax(key_t64 &k, int j, bool keep_min)
+{
+    const key_t64 o = __shfl_xor_sync(0xffffffffu, k, j);
+    if ((o < k) == keep_min) k = o;
 }
 
-__device__ __forceinline__ void warp_minmax(float &d, int &i, int j, bool keep_min)
+// ascending bitonic sort of one key per lane
+__device__ __forceinline__ void warp_sort(key_t64 &k, int lane)
 {
-    const float od = __shfl_xor_sync(0xffffffffu, d, j);
-    const int oi = __shfl_xor_sync(0xffffffffu, i, j);
-    const bool other_less = pair_less(od, oi, d, i);
-    if (other_less == keep_min) {
-        d = od;
-        i = oi;
+#pragma unroll
+    for (int kk = 2; kk <= 32; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const bool up = (lane & kk) == 0;
+            warp_minmax(k, j, ((lane & j) == 0) == up);
+        }
     }
 }
 
-// ascending bitonic sort of one (d,i) pair per lane
-__device__ __forceinline__ void warp_sort(float &d, int &i, int lane)
+// Offer one batch (one candidate key per lane, KEY_INVALID where none) to the lane-distributed
+// sorted list `mine`; only candidates below the current K-th entry can matter.
+__device__ __forceinline__ void warp_list_offer(key_t64 &mine, key_t64 cand, int K, int lane, bool &list_empty)
 {
+    const unsigned FULL = 0xffffffffu;
+    if (list_empty) {   // first batch: sort it straight into the list
+        warp_sort(cand, lane);
+        mine = (cand < KEY_EMPTY) ? cand : KEY_EMPTY;
+        list_empty = false;
+        return;
+    }
+    const key_t64 thr = __shfl_sync(FULL, mine, K - 1);
+    unsigned mask = __ballot_sync(FULL, cand < thr);
+    if (__popc(mask) > 12) {
+        // many newcomers: sort the batch, keep the 32 smallest of list U batch
+        warp_sort(cand, lane);
+        const key_t64 rev = __shfl_sync(FULL, cand, 31 - lane);
+        if (rev < mine) mine = rev;
 #pragma unroll
-    for (int k = 2; k <= 32; k <<= 1) {
-#pragma unroll
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            const bool up = (lane & k) == 0;
-            warp_minmax(d, i, j, ((lane & j) == 0) == up);
+        for (int jj = 16; jj > 0; jj >>= 1) warp_minmax(mine, jj, (lane & jj) == 0);
+        if (mine > KEY_EMPTY) mine = KEY_EMPTY;
+    } else {
+        while (mask) {   // shift-insert one candidate
+            const int src = __ffs(mask) - 1;
+            mask &= mask - 1;
+            const key_t64 x = __shfl_sync(FULL, cand, src);
+            const key_t64 pred = __shfl_up_sync(FULL, mine, 1);
+            if (x < mine) mine = (lane > 0 && x < pred) ? pred : x;   // mine sorts after x: shift or take x
         }
     }
 }
@@ -683,35 +721,39 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
         return m;
     };
 
-    float my_d = INF;   // lane j: j-th best so far
-    int my_i = 0;
+    key_t64 mine = KEY_EMPTY;   // lane j: j-th best so far
+    bool list_empty = true;
     bool done = false;
     int r = (out > (float)RMAX * h) ? RMAX + 1 : 1;
+    int e_prev = 0;                  // rows [0, e_prev) of the table were scanned over cells [px0, px1]
+    int px0 = 0, px1 = -1;
     while (r <= RMAX) {
-        my_d = INF;
-        my_i = 0;
-        bool list_empty = true;
         const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
         const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
         const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
         const int e_end = (2 * r + 1) * (2 * r + 1);
-        // row groups, centre-out: {centre + 4 adjacent}, {4 diagonal}, ring 2, ring 3, ring 4
-        for (int g = 0; g < 5; ++g) {
-            const int gs = (g == 0) ? 0 : (g == 1) ? 5 : (g == 2) ? 9 : (g == 3) ? 25 : 49;
-            const int ge = (g == 0) ? 5 : (g == 1) ? 9 : (g == 2) ? 25 : (g == 3) ? 49 : 81;
-            if (gs >= e_end) break;
-            const float kth_now = __shfl_sync(FULL, my_d, K - 1);   // +inf until K candidates were seen
-            const int e = gs + lane;
+        // segments: two per old row (its new end cells), one per new row (all its cells)
+        const int nseg = 2 * e_prev + (e_end - e_prev);
+        for (int s0 = 0; s0 < nseg; s0 += 32) {
+            const float kth_now = key_dist(__shfl_sync(FULL, mine, K - 1));   // +inf until K were seen
+            const int sidx = s0 + lane;
             int beg = 0, end = 0;
-            if (e < ge) {
+            if (sidx < nseg) {
+                const bool old = sidx < 2 * e_prev;
+                const int e = old ? (sidx >> 1) : (sidx - e_prev);
                 const int z = cz + kRowOrder[e][0], y = cy + kRowOrder[e][1];
-                if (z >= z0 && z <= z1 && y >= y0 && y <= y1) {
+                int a = x0, c = x1;   // cell range of this segment
+                if (old) {
+                    if (sidx & 1) a = px1 + 1;   // right end
+                    else c = px0 - 1;            // left end
+                }
+                if (z >= z0 && z <= z1 && y >= y0 && y <= y1 && a <= c) {
                     // rows that cannot hold anything closer than the current K-th best are skipped
                     const float dmin2 = slab_dist2(qy, Ps.lo[1], h, y, slack) + slab_dist2(qz, Ps.lo[2], h, z, slack);
                     if (!(dmin2 > kth_now)) {
                         const int row = (z * ny + y) * nx;
-                        beg = (row + x0 > 0) ? __ldg(cell_end + row + x0 - 1) : 0;
-                        end = __ldg(cell_end + row + x1);
+                        beg = (row + a > 0) ? __ldg(cell_end + row + a - 1) : 0;
+                        end = __ldg(cell_end + row + c);
                     }
                 }
             }
@@ -726,7 +768,7 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
             const int excl = incl - cnt;
             for (int j0 = 0; j0 < total; j0 += 32) {
                 const int j = j0 + lane;
-                int seg = 0;   // number of rows whose inclusive count is <= j
+                int seg = 0;   // number of segments whose inclusive count is <= j
 #pragma unroll
                 for (int step = 16; step > 0; step >>= 1) {
                     const int v = __shfl_sync(FULL, incl, seg + step - 1);
@@ -734,57 +776,19 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
                 }
                 const int sb = __shfl_sync(FULL, beg, seg);
                 const int se = __shfl_sync(FULL, excl, seg);
-                const bool valid = j < total;
-                float cd = INF;
-                int ci = 0x7fffffff;
-                if (valid) {
+                key_t64 cand = KEY_INVALID;
+                if (j < total) {
                     const float4 c = __ldg(sorted + sb + (j - se));
-                    cd = ref_sqdist(qx, qy, qz, c.x, c.y, c.z);
-                    ci = __float_as_int(c.w);
+                    cand = make_key(ref_sqdist(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
                 }
-                if (list_empty) {   // first batch: sort it straight into the list
-                    warp_sort(cd, ci, lane);
-                    my_d = cd;
-                    my_i = (cd < INF) ? ci : 0;
-                    list_empty = false;
-                    continue;
-                }
-                const float thr_d = __shfl_sync(FULL, my_d, K - 1);
-                const int thr_i = __shfl_sync(FULL, my_i, K - 1);
-                const bool acc = valid && pair_less(cd, ci, thr_d, thr_i);
-                unsigned mask = __ballot_sync(FULL, acc);
-                if (__popc(mask) > 12) {
-                    // many newcomers: sort the batch, keep the 32 smallest of list U batch
-                    warp_sort(cd, ci, lane);
-                    const float rd = __shfl_sync(FULL, cd, 31 - lane);
-                    const int ri = __shfl_sync(FULL, ci, 31 - lane);
-                    if (pair_less(rd, ri, my_d, my_i)) {
-                        my_d = rd;
-                        my_i = ri;
-                    }
-#pragma unroll
-                    for (int jj = 16; jj > 0; jj >>= 1) warp_minmax(my_d, my_i, jj, (lane & jj) == 0);
-                    if (!(my_d < INF)) my_i = 0;
-                } else {
-                    while (mask) {   // shift-insert one candidate
-                        const int src = __ffs(mask) - 1;
-                        mask &= mask - 1;
-                        const float xd = __shfl_sync(FULL, cd, src);
-                        const int xi = __shfl_sync(FULL, ci, src);
-                        const float pd = __shfl_up_sync(FULL, my_d, 1);
-                        const int pi = __shfl_up_sync(FULL, my_i, 1);
-                        const bool gt = pair_less(xd, xi, my_d, my_i);               // mine sorts after x
-                        const bool pgt = lane > 0 && pair_less(xd, xi, pd, pi);      // so does my predecessor
-                        if (gt) {
-                            my_d = pgt ? pd : xd;
-                            my_i = pgt ? pi : xi;
-                        }
-                    }
-                }
+                warp_list_offer(mine, cand, K, lane, list_empty);
             }
         }
+        e_prev = e_end;
+        px0 = x0;
+        px1 = x1;
         const float m = margin(r);
-        const float kth = __shfl_sync(FULL, my_d, K - 1);
+        const float kth = key_dist(__shfl_sync(FULL, mine, K - 1));
         if (m == INF) {
             done = true;
             break;
@@ -804,7 +808,7 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
         r = rn;
     }
     if (done) {
-        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)my_i;
+        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)(unsigned)(mine & 0xffffffffu);
         return;
     }
     if (lane == 0) {
@@ -885,61 +889,26 @@ grid_overflow_warp_kernel(const float *__restrict__ support, const float *__rest
                           int Q, int K, const QueryState *__restrict__ state_all,
                           const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
 {
-    const unsigned FULL = 0xffffffffu;
     const int b = blockIdx.y;
     const int count = state_all[b].ovf_count;
     const int lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const float *sup = support + (size_t)b * S * 3;
-    const float INF = __int_as_float(0x7f800000);
     for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < count; t += gridDim.x * wpb) {
         const int q = ovf_all[(size_t)b * Q + t];
         const float *qp = query + ((size_t)b * Q + q) * 3;
         const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
-        float my_d = INF;
-        int my_i = 0;
+        key_t64 mine = KEY_EMPTY;
+        bool list_empty = true;
         for (int s0 = 0; s0 < S; s0 += 32) {
             const int sI = s0 + lane;
-            const bool valid = sI < S;
-            float cd = INF;
-            int ci = 0x7fffffff;
-            if (valid) {
-                cd = ref_sqdist(qx, qy, qz, __ldg(sup + (size_t)sI * 3), __ldg(sup + (size_t)sI * 3 + 1),
-                                __ldg(sup + (size_t)sI * 3 + 2));
-                ci = sI;
-            }
-            const float thr_d = __shfl_sync(FULL, my_d, K - 1);
-            const int thr_i = __shfl_sync(FULL, my_i, K - 1);
-            unsigned mask = __ballot_sync(FULL, valid && pair_less(cd, ci, thr_d, thr_i));
-            if (__popc(mask) > 12) {
-                warp_sort(cd, ci, lane);
-                const float rd = __shfl_sync(FULL, cd, 31 - lane);
-                const int ri = __shfl_sync(FULL, ci, 31 - lane);
-                if (pair_less(rd, ri, my_d, my_i)) {
-                    my_d = rd;
-                    my_i = ri;
-                }
-#pragma unroll
-                for (int jj = 16; jj > 0; jj >>= 1) warp_minmax(my_d, my_i, jj, (lane & jj) == 0);
-                if (!(my_d < INF)) my_i = 0;
-            } else {
-                while (mask) {
-                    const int src = __ffs(mask) - 1;
-                    mask &= mask - 1;
-                    const float xd = __shfl_sync(FULL, cd, src);
-                    const int xi = __shfl_sync(FULL, ci, src);
-                    const float pd = __shfl_up_sync(FULL, my_d, 1);
-                    const int pi = __shfl_up_sync(FULL, my_i, 1);
-                    const bool gt = pair_less(xd, xi, my_d, my_i);
-                    const bool pgt = lane > 0 && pair_less(xd, xi, pd, pi);
-                    if (gt) {
-                        my_d = pgt ? pd : xd;
-                        my_i = pgt ? pi : xi;
-                    }
-                }
-            }
+            key_t64 cand = KEY_INVALID;
+            if (sI < S)
+                cand = make_key(ref_sqdist(qx, qy, qz, __ldg(sup + (size_t)sI * 3), __ldg(sup + (size_t)sI * 3 + 1),
+                                           __ldg(sup + (size_t)sI * 3 + 2)), sI);
+            warp_list_offer(mine, cand, K, lane, list_empty);
         }
-        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)my_i;
+        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)(unsigned)(mine & 0xffffffffu);
     }
 }
 

@@ -60,6 +60,14 @@ class FusionPass:
         return ops.choose_gather(feat.reshape(self.B, C, self.h, self.w) if self.layout == "nchw"
                                  else feat.squeeze(3), idx)
 
+    def kernel_of(self, i):
+        """Name of the CUDA kernel the i-th gather of the schedule runs on."""
+        from ._lib import lib, LAYOUT_NCS, LAYOUT_NSC
+        op, key, C, Sz, Q, K = self.gathers[i]
+        k = 1 if op != "random_sample" else self.k
+        lay = LAYOUT_NCS if self.layout == "nchw" else LAYOUT_NSC
+        return lib.ffb6d_gather_kernel_name(self.B, C, Sz, Q, k, lay).decode()
+
     def run_gathers(self, inputs, timer=None):
         n = len(self.gathers)
         outs = [None] * n
@@ -67,7 +75,7 @@ class FusionPass:
             for i, ((op, key, C, Sz, Q, K), feat) in enumerate(zip(self.gathers, self.features)):
                 idx = inputs[key]
                 if timer is not None:
-                    timer.start("gather:%s" % key,
+                    timer.start("gather:%s:%s" % (key, self.kernel_of(i)),
                                 S.gather_alg_bytes(C, Sz, Q, idx.shape[-1] if op != "choose" else 1) * self.B)
                 outs[i] = self._gather(op, C, feat, idx)
                 if timer is not None:

@@ -138,6 +138,8 @@ int ffb6d_knn_host(const float *points, size_t npts, size_t dim,
 int ffb6d_gather_max_fwd(const float *feat, const void *idx, int idx_is_i64,
                          int64_t B, int64_t C, int64_t S, int64_t Q, int K,
                          int layout, float *out, ffb6d_stream_t stream);
+/* Name of the kernel ffb6d_gather_max_fwd launches for a shape (for profiling tools). */
+const char *ffb6d_gather_kernel_name(int64_t B, int64_t C, int64_t S, int64_t Q, int K, int layout);
 /*
  * Backward of the above as autograd defines it for gather + max: grad_feat is
  * zero-filled, then grad_out[b,c,q] is added at the arg-max neighbour (the first
