@@ -326,6 +326,69 @@ def relative_pos_encoding(xyz, neigh_idx):
     return out
 
 
+# --------------------------------------------------------------------------- depth -> point sets
+def backproject(depth, K, choose):
+    """Depth map -> the point sets of the fusion schedule, on the GPU; replaces ``dpt_2_pcld`` +
+    the ``choose`` sampling + the stride pyramids of the datasets
+    (datasets/ycb/ycb_dataset.py:165-176, 237, 253-267), bit-identically (float64 math, one
+    rounding to float32).
+
+    :param depth: ``[B,H,W]`` float32 CUDA, metres, 0 at holes (``dpt_m`` of the datasets)
+    :param K: camera matrix ``[3,3]`` (shared) or ``[B,3,3]``, anything ``np.asarray`` accepts
+    :param choose: ``[B,1,N]`` or ``[B,N]`` int32/int64 flat pixel indices of the sampled points
+    :return: ``(cld [B,N,3], {2: [B,HW/4,3], 4: [B,HW/16,3], 8: [B,HW/64,3]})`` float32
+    """
+    _need_cuda(depth, "depth")
+    _need_cuda(choose, "choose")
+    if depth.dim() != 3 or depth.dtype != torch.float32:
+        raise ValueError("depth must be float32 [B,H,W], got %s %s" % (depth.dtype, tuple(depth.shape)))
+    depth = depth.contiguous()
+    B, H, W = depth.shape
+    dev = depth.device
+    if isinstance(K, torch.Tensor) and K.is_cuda:
+        # (fx, fy, cx, cy) already on the device: [4] shared or [B,4] (no host copy: graph-capturable)
+        if K.dtype != torch.float64 or K.shape not in ((4,), (B, 4)):
+            raise ValueError("device intrinsics must be float64 [4] or [B,4] = (fx, fy, cx, cy)")
+        intr_d, per_frame = K.contiguous(), int(K.dim() == 2)
+        return _backproject(depth, intr_d, per_frame, choose)
+    Kn = np.asarray(K, dtype=np.float64)
+    if Kn.shape == (3, 3):
+        intr = np.array([Kn[0, 0], Kn[1, 1], Kn[0, 2], Kn[1, 2]], np.float64)
+        per_frame = 0
+    elif Kn.shape == (B, 3, 3):
+        intr = np.stack([Kn[:, 0, 0], Kn[:, 1, 1], Kn[:, 0, 2], Kn[:, 1, 2]], 1).copy()
+        per_frame = 1
+    else:
+        raise ValueError("K must be [3,3] or [B,3,3], got %s" % (Kn.shape,))
+    return _backproject(depth, torch.from_numpy(intr).to(dev), per_frame, choose)
+
+
+def intrinsics_to_device(K, device, batch=None):
+    """Camera matrix ``[3,3]`` / ``[B,3,3]`` -> float64 ``[4]`` / ``[B,4]`` (fx, fy, cx, cy) on the device."""
+    Kn = np.asarray(K, dtype=np.float64)
+    if Kn.ndim == 2:
+        v = np.array([Kn[0, 0], Kn[1, 1], Kn[0, 2], Kn[1, 2]], np.float64)
+    else:
+        v = np.stack([Kn[:, 0, 0], Kn[:, 1, 1], Kn[:, 0, 2], Kn[:, 1, 2]], 1).copy()
+    return torch.from_numpy(v).to(device)
+
+
+def _backproject(depth, intr_d, per_frame, choose):
+    B, H, W = depth.shape
+    dev = depth.device
+    ch = choose.reshape(B, -1)
+    if ch.dtype != torch.int32 or not ch.is_contiguous():
+        ch = ch.to(torch.int32).contiguous()
+    N = ch.shape[1]
+    cld = torch.empty((B, N, 3), dtype=torch.float32, device=dev)
+    pyr = {s: torch.empty((B, (H // s) * (W // s), 3), dtype=torch.float32, device=dev) for s in (2, 4, 8)}
+    with torch.cuda.device(dev):
+        check(lib.ffb6d_backproject(depth.data_ptr(), B, H, W, intr_d.data_ptr(), per_frame, ch.data_ptr(), N,
+                                    cld.data_ptr(), pyr[2].data_ptr(), pyr[4].data_ptr(), pyr[8].data_ptr(),
+                                    _stream(dev)))
+    return cld, pyr
+
+
 # --------------------------------------------------------------------------- grid subsampling
 def grid_sub_sampling(points, features=None, labels=None, grid_size=0.1, verbose=0):
     """Voxel-grid barycentre subsampling; mirrors ``DataProcessing.grid_sub_sampling``

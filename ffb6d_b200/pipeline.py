@@ -95,31 +95,39 @@ class FusionPass:
         return outs
 
     # -- CUDA-graph replay: the pass is ~200 small launches with static shapes ----------
-    def capture(self, cld, dpt_xyz, choose, host_inputs=None, digest=None):
-        """Capture one pass into a CUDA graph and return ``replay()``.
+    def capture(self, fn, copies=(), digest=None, prefetch=()):
+        """Capture ``fn()`` (a closure over static device buffers that runs a pass and returns its
+        result) into a CUDA graph and return ``replay()``.
 
-        ``cld/dpt_xyz/choose`` are the static device buffers the graph reads.  With
-        ``host_inputs=(cld_h, xyz_h, choose_h)`` (pinned) the graph starts with the three H2D
-        copies, and with ``digest=(fn, pinned_out)`` it ends with ``pinned_out.copy_(fn(inputs,
-        outs))`` -- the end-to-end variant bench.py times.  ``replay()`` returns (inputs, outs)
-        of the captured pass (tensors owned by the graph's memory pool)."""
+        ``copies``: ``(dst_device, src_pinned_host)`` pairs copied at the start of the graph, on the
+        main stream, before ``fn``.  ``prefetch``: pairs copied on a side stream concurrently with
+        ``fn`` (inputs of the NEXT replay: double buffering).  ``digest=(f, pinned_out)``:
+        ``pinned_out.copy_(f(*result))`` at the end (the D2H read of the end-to-end variant)."""
+        side = torch.cuda.Stream(device=self.device)
+
         def body():
-            if host_inputs is not None:
-                cld.copy_(host_inputs[0], non_blocking=True)
-                dpt_xyz.copy_(host_inputs[1], non_blocking=True)
-                choose.copy_(host_inputs[2], non_blocking=True)
-            res = self(cld, dpt_xyz, choose)
+            main = torch.cuda.current_stream(self.device)
+            for dst, src in copies:
+                dst.copy_(src, non_blocking=True)
+            if prefetch:
+                side.wait_stream(main)
+                with torch.cuda.stream(side):
+                    for dst, src in prefetch:
+                        dst.copy_(src, non_blocking=True)
+            res = fn()
+            if prefetch:
+                main.wait_stream(side)
             if digest is not None:
                 d = digest[0](*res)
                 digest[1][: d.numel()].copy_(d, non_blocking=True)
             return res
 
-        side = torch.cuda.Stream(device=self.device)
-        side.wait_stream(torch.cuda.current_stream(self.device))
-        with torch.cuda.stream(side):
+        warm = torch.cuda.Stream(device=self.device)
+        warm.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.stream(warm):
             for _ in range(2):        # allocator + lazy one-time settings happen outside the capture
                 body()
-        torch.cuda.current_stream(self.device).wait_stream(side)
+        torch.cuda.current_stream(self.device).wait_stream(warm)
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(graph):
@@ -131,6 +139,14 @@ class FusionPass:
 
         replay.graph = graph
         return replay
+
+    def from_depth(self, depth, intr, choose):
+        """depth [B,H,W] f32, intr = device (fx,fy,cx,cy) float64 [4]|[B,4], choose [B,1,N] -> pass."""
+        cld, pyr = ops.backproject(depth, intr, choose)
+        inputs = S.build_ffb6d_indices(cld, None, k=self.k, index_dtype=self.index_dtype, streams=self.streams,
+                                       pyramid=pyr, image_hw=(self.h, self.w))
+        inputs["choose"] = choose
+        return inputs, self.run_gathers(inputs)
 
     def __call__(self, cld, dpt_xyz, choose, timer=None):
         """cld [B,N0,3] f32, dpt_xyz [B,H,W,3] f32, choose [B,1,N0] int -> (inputs dict, outputs)."""

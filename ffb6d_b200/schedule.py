@@ -115,11 +115,14 @@ def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
     return pyr
 
 
-def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None):
+def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None,
+                        pyramid=None, image_hw=None):
     """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
 
     :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
-    :param dpt_xyz: ``[B, H, W, 3]`` float32 CUDA, the organised cloud (zero rows at holes)
+    :param dpt_xyz: ``[B, H, W, 3]`` float32 CUDA, the organised cloud (zero rows at holes); or
+      pass ``pyramid={2: [B,HW/4,3], 4: ..., 8: ...}`` + ``image_hw=(H, W)`` (what
+      :func:`ffb6d_b200.ops.backproject` returns) and leave it None
     :param streams: optional list of side ``torch.cuda.Stream`` s to overlap the 22 searches on
     :param timer: optional object with ``start(name, alg_bytes)`` / ``stop()`` called around
       every KNN call (bench.py's per-op CUDA-event timer)
@@ -134,13 +137,21 @@ def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=
     "Random sampling" is the reference's: the cloud was shuffled once, every level keeps the
     first quarter of the previous one (ycb_dataset.py:233-235, 278).
     """
-    if cld.dim() != 3 or dpt_xyz.dim() != 4 or cld.shape[0] != dpt_xyz.shape[0]:
-        raise ValueError("expected cld [B,N,3] and dpt_xyz [B,H,W,3]")
+    if cld.dim() != 3 or cld.shape[2] != 3:
+        raise ValueError("expected cld [B,N,3]")
     cld = cld.contiguous().float()
     B, n0, _ = cld.shape
-    H, W = dpt_xyz.shape[1], dpt_xyz.shape[2]
     used = sorted(set(RGB_DS_SR) | set(RGB_UP_SR))          # sr=1 is never searched
-    sets = {("img", sr): p for sr, p in image_pyramid(dpt_xyz.float(), used).items()}
+    if pyramid is not None:
+        if image_hw is None:
+            raise ValueError("image_hw=(H, W) is required with pyramid=")
+        H, W = image_hw
+        sets = {("img", sr): pyramid[sr] for sr in used}
+    else:
+        if dpt_xyz is None or dpt_xyz.dim() != 4 or cld.shape[0] != dpt_xyz.shape[0]:
+            raise ValueError("expected dpt_xyz [B,H,W,3] (or pyramid=)")
+        H, W = dpt_xyz.shape[1], dpt_xyz.shape[2]
+        sets = {("img", sr): p for sr, p in image_pyramid(dpt_xyz.float(), used).items()}
     n = n0
     for i in range(N_DS_LAYERS + 1):
         sets[("cld", i)] = cld if i == 0 else cld[:, :n, :].contiguous()
@@ -200,3 +211,14 @@ def build_ffb6d_indices(cld, dpt_xyz, k=K_NEIGH, index_dtype=torch.int32, timer=
         n_sub = sets[("cld", i + 1)].shape[1]
         inputs["cld_sub_idx%d" % i] = inputs["cld_nei_idx%d" % i][:, :n_sub, :].contiguous()
     return inputs
+
+
+def build_ffb6d_indices_from_depth(depth, K, choose, k=K_NEIGH, index_dtype=torch.int32, streams=None):
+    """Depth map in, all index tensors out: back-projection, sampling and stride pyramids
+    (datasets/ycb/ycb_dataset.py:165-176, 237, 253-267) followed by the 22 searches, everything on
+    the GPU.  ``depth [B,H,W]`` float32 metres, ``K`` camera matrix, ``choose [B,1,N]`` pixel
+    indices of the sampled points.  Returns the dict of :func:`build_ffb6d_indices`."""
+    from .ops import backproject
+    cld, pyr = backproject(depth, K, choose)
+    return build_ffb6d_indices(cld, None, k=k, index_dtype=index_dtype, streams=streams, pyramid=pyr,
+                               image_hw=(depth.shape[1], depth.shape[2]))

@@ -33,7 +33,7 @@ def depth_to_xyz(dpt, K):
 
 def make_frame(seed, n_points=12288, h=480, w=640, hole_frac=0.1, intrinsics="linemod"):
     """One synthetic frame.  Returns a dict with ``dpt_xyz [H,W,3] f32``, ``cld [N,3] f32``,
-    ``choose [1,N] int32``, ``cld_rgb_nrm [9,N] f32`` (xyz | rgb in [0,255) | unit normals)."""
+    ``choose [1,N] int32``, ``depth [H,W] f32`` (metres, 0 at holes), ``cld_rgb_nrm [9,N] f32`` (xyz | rgb in [0,255) | unit normals)."""
     rs = np.random.RandomState(seed)
     ys, xs = np.mgrid[:h, :w]
     d = 0.8 + 0.3 * np.sin(xs / 57.0) * np.cos(ys / 43.0) + 0.02 * rs.rand(h, w)
@@ -49,7 +49,7 @@ def make_frame(seed, n_points=12288, h=480, w=640, hole_frac=0.1, intrinsics="li
     rgb = rs.uniform(0, 255, (n_points, 3)).astype(np.float32)
     nrm = rs.normal(size=(n_points, 3))
     nrm = (nrm / np.linalg.norm(nrm, axis=1, keepdims=True)).astype(np.float32)
-    return dict(dpt_xyz=xyz, cld=cld, choose=choose[None, :],
+    return dict(dpt_xyz=xyz, cld=cld, choose=choose[None, :], depth=d,
                 cld_rgb_nrm=np.concatenate((cld, rgb, nrm), axis=1).T.copy())
 
 

@@ -175,6 +175,21 @@ int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_i
                                     int64_t B, int64_t N, int K,
                                     float *out, ffb6d_stream_t stream);
 
+/* ---- depth map -> searched point sets ------------------------------------- */
+/*
+ * Back-projection of the depth image and extraction of the four point sets the fusion
+ * schedule searches, replacing dpt_2_pcld + the `choose` sampling + the stride pyramids of the
+ * datasets (datasets/ycb/ycb_dataset.py:165-176, 237, 253-267).  float64 arithmetic like numpy's,
+ * rounded once to float32: bit-identical to the reference's arrays.
+ *   depth [B,H,W] f32 metres (0 = hole), intrinsics (fx, fy, cx, cy) as float64: 4 values shared
+ *   by the batch (intrinsics_per_frame = 0) or [B,4]; choose [B,N] int32 flat pixel indices
+ *   -> cld [B,N,3]; pyr2 [B,(H/2)*(W/2),3]; pyr4; pyr8   (f32; holes are signed zeros)
+ */
+int ffb6d_backproject(const float *depth, int64_t B, int64_t H, int64_t W,
+                      const double *intrinsics, int intrinsics_per_frame,
+                      const int *choose, int64_t N,
+                      float *cld, float *pyr2, float *pyr4, float *pyr8, ffb6d_stream_t stream);
+
 /* ---- grid subsampling --------------------------------------------------- */
 /*
  * Voxel-grid barycentre subsampling, replaces grid_subsampling()

@@ -159,6 +159,35 @@ def grid_cases():
     return cases
 
 
+def backproject_digest():
+    """sha256 of float32(dpt_2_pcld(depth)) computed by the reference's own method
+    (datasets/ycb/ycb_dataset.py:165-176, executed from its source text) for synthetic depth maps."""
+    import ast
+    path = os.path.join(R.REF_ROOT, "ffb6d", "datasets", "ycb", "ycb_dataset.py")
+    tree = ast.parse(open(path).read())
+    fn = None
+    for node in ast.walk(tree):
+        if isinstance(node, ast.FunctionDef) and node.name == "dpt_2_pcld":
+            ns = {"np": np}
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            fn = ns["dpt_2_pcld"]
+    assert fn is not None
+
+    class _Self:   # ycb_dataset.py:31-32
+        xmap = np.array([[j for i in range(640)] for j in range(480)])
+        ymap = np.array([[i for i in range(640)] for j in range(480)])
+
+    from ffb6d_b200.synthetic import INTRINSICS
+    out = {}
+    for seed, intr in ((0, "linemod"), (7, "ycb_K1")):
+        fr = make_frame(seed, n_points=768, intrinsics=intr)
+        xyz = fn(_Self(), fr["depth"], 1.0, INTRINSICS[intr]).astype(np.float32)
+        assert np.array_equal(xyz, fr["dpt_xyz"])        # the synthetic generator restates the same lines
+        out["seed%d_%s" % (seed, intr)] = {"seed": seed, "intrinsics": intr, "sha256_xyz_f32": sha(xyz),
+                                           "sha256_depth": sha(fr["depth"])}
+    return out
+
+
 def main():
     if not R.reference_sources_present():
         raise SystemExit("needs /root/reference")
@@ -172,6 +201,8 @@ def main():
                                                     "keys": schedule_digest(seed, n)}
     with open(os.path.join(OUT, "schedule_digest.json"), "w") as fh:
         json.dump(dig, fh, indent=1, sort_keys=True)
+    with open(os.path.join(OUT, "backproject_digest.json"), "w") as fh:
+        json.dump(backproject_digest(), fh, indent=1, sort_keys=True)
     print("golden fixtures written to", OUT)
 
 

@@ -83,3 +83,17 @@ def test_shape_errors():
         ops.knn_search(np.zeros((1, 4, 3), np.float32), np.zeros((2, 4, 3), np.float32), 2)
     with pytest.raises(RuntimeError):
         ops.grid_sub_sampling(np.zeros((4, 2), np.float32))
+
+
+def test_synthetic_backprojection_is_the_references():
+    """make_frame's organised cloud == the reference's dpt_2_pcld on the same depth map (digest made
+    by tests/golden/make_golden.py from the reference's own source)."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN
+    d = json.load(open(os.path.join(GOLDEN, "backproject_digest.json")))
+    for case in d.values():
+        fr = synthetic.make_frame(case["seed"], n_points=768, intrinsics=case["intrinsics"])
+        assert hashlib.sha256(np.ascontiguousarray(fr["depth"]).tobytes()).hexdigest() == case["sha256_depth"]
+        assert hashlib.sha256(np.ascontiguousarray(fr["dpt_xyz"]).tobytes()).hexdigest() == case["sha256_xyz_f32"]
