@@ -169,7 +169,7 @@ def cpu_reference_sample(n_points, frames_knn, frames_gather, reps=1):
             "t_knn": t_knn, "t_gather": t_g}
 
 
-def run_reference_arm(args, rank):
+def run_reference_arm(args, rank, emit):
     if rank != 0:
         return 0
     cores = os.cpu_count() or 1
@@ -198,7 +198,7 @@ def run_reference_arm(args, rank):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "wall_s": wall,
     }
-    print(json.dumps(line))
+    emit(line)
     return 0
 
 
@@ -253,8 +253,18 @@ def main():
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
     rank, local_rank, world = env_int("RANK", 0), env_int("LOCAL_RANK", 0), env_int("WORLD_SIZE", 1)
+    # stdout carries exactly one JSON line: libraries that print to fd 1 (NCCL's version banner)
+    # are sent to stderr for the duration of the run
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
+
     if args.impl == "reference":
-        return run_reference_arm(args, rank)
+        return run_reference_arm(args, rank, emit)
 
     import numpy as np
     import torch
@@ -391,14 +401,21 @@ def main():
     # behind the CPU so the events bracket kernel time, not Python launch gaps.
     timer = OpTimer()
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    inst_ms = 0.0
+    s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    inst_ms, spin_ms, enqueue_ms = 0.0, 0.0, 0.0
+    spin_cycles = int(2.0e9 * 0.004 * max(4.0, ms / args.steps))   # ~4x a step: the CPU gets a head start
     for _ in range(args.steps):
-        torch.cuda._sleep(int(40e6))
+        s0.record()
+        torch.cuda._sleep(spin_cycles)
+        s1.record()
         i0.record()
+        c0 = time.perf_counter()
         p(cld_d, xyz_d, cho_d, timer)
+        enqueue_ms += (time.perf_counter() - c0) * 1e3
         i1.record()
         torch.cuda.synchronize()
         inst_ms += i0.elapsed_time(i1)
+        spin_ms += s0.elapsed_time(s1)
     clocks = sampler.stop() if sampler is not None else None
 
     # ---- max over ranks (device time, never wall clock of one rank)
@@ -476,10 +493,12 @@ def main():
                         "activations as in the reference (the network produces them on the GPU)"},
         "gpu_launches": int(launches), "cuda_graph": bool(use_graph),
         "instrumented_ms_per_step": inst_ms / steps, "sum_of_ops_ms_per_step": tot_ms / steps,
+        "instrumented_note": "eager launches + per-op events behind a %.1f ms spin kernel; the CPU needs %.1f ms to "
+                             "enqueue a step" % (spin_ms / steps, enqueue_ms / steps),
         "roofline": roofline, "pass_roofline": pass_roofline,
         "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
     return 0

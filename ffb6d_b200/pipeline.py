@@ -155,15 +155,24 @@ class FusionPass:
 
 
 class OpTimer:
-    """CUDA-event pair per op on the current stream; durations are read after a synchronize."""
+    """CUDA-event pair per op on the current stream; durations are read after a synchronize.
+    Events come from a pool created up front so that recording costs the CPU as little as possible."""
 
-    def __init__(self):
+    def __init__(self, pool=4096):
         self.records = []          # (name, alg_bytes, start_event, stop_event)
         self._cur = None
+        self._pool = [torch.cuda.Event(enable_timing=True) for _ in range(pool)]
+        self._next = 0
+
+    def _event(self):
+        if self._next >= len(self._pool):
+            self._pool.extend(torch.cuda.Event(enable_timing=True) for _ in range(1024))
+        e = self._pool[self._next]
+        self._next += 1
+        return e
 
     def start(self, name, alg_bytes):
-        e0 = torch.cuda.Event(enable_timing=True)
-        e1 = torch.cuda.Event(enable_timing=True)
+        e0, e1 = self._event(), self._event()
         e0.record()
         self._cur = (name, alg_bytes, e0, e1)
 
@@ -174,7 +183,7 @@ class OpTimer:
         self._cur = None
 
     def summary(self):
-        """{name: {"ms": total, "bytes": total alg bytes, "launches": n}} (call after synchronize)."""
+        """{name: {"ms": total, "bytes": total alg bytes, "n": launches}} (call after synchronize)."""
         out = {}
         for name, b, e0, e1 in self.records:
             d = out.setdefault(name, {"ms": 0.0, "bytes": 0, "n": 0})
