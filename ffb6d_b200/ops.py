@@ -326,6 +326,60 @@ def relative_pos_encoding(xyz, neigh_idx):
     return out
 
 
+# --------------------------------------------------------------------------- fusion 1x1 MLP
+def fold_batchnorm(bn):
+    """Eval-mode BatchNorm as a per-channel affine: ``scale = gamma / sqrt(var + eps)``,
+    ``shift = beta - mean * scale`` (float32 tensors on the module's device)."""
+    var, mean = bn.running_var.float(), bn.running_mean.float()
+    gamma = bn.weight.float() if bn.weight is not None else torch.ones_like(var)
+    beta = bn.bias.float() if bn.bias is not None else torch.zeros_like(var)
+    scale = gamma / torch.sqrt(var + bn.eps)
+    return scale.contiguous(), (beta - mean * scale).contiguous()
+
+
+def fusion_mlp(x1, x2, weight, scale, shift, relu=True):
+    """``relu(scale * conv1x1(cat(x1, x2, dim=1)) + shift)`` in one tensor-core kernel
+    (``ffb6d_fusion_mlp_fwd``): the fusion layers of FFB6D (models/ffb6d.py:55-80, 104-129 applied
+    at :246-262, 282-298: ``torch.cat`` -> ``pt_utils.Conv2d(1x1, bias=False)`` -> BatchNorm -> ReLU)
+    with frozen BatchNorm statistics.  Inference only (no backward).
+
+    :param x1: ``[B, C1, N, 1]`` / ``[B, C1, H, W]`` / ``[B, C1, N]`` float32 CUDA, NCHW-contiguous
+    :param x2: second input of the concat with the same trailing shape, or ``None``
+    :param weight: ``[Co, C1+C2]`` or ``[Co, C1+C2, 1, 1]`` (``conv.weight``)
+    :param scale, shift: ``[Co]`` folded BatchNorm (:func:`fold_batchnorm`); pass ones / the conv
+      bias for a layer without BatchNorm
+    :return: ``[B, Co, ...]`` with the trailing shape of ``x1``
+    """
+    _need_cuda(x1, "x1")
+    if x1.dtype != torch.float32:
+        raise TypeError("x1 must be float32")
+    B, C1 = x1.shape[0], x1.shape[1]
+    tail = tuple(x1.shape[2:])
+    x1c = x1.contiguous()
+    P = x1c.numel() // max(B * C1, 1)
+    C2 = 0
+    x2c = None
+    if x2 is not None:
+        _need_cuda(x2, "x2")
+        if x2.dtype != torch.float32 or x2.shape[0] != B or tuple(x2.shape[2:]) != tail:
+            raise ValueError("x2 must be float32 with the batch and trailing shape of x1")
+        x2c = x2.contiguous()
+        C2 = x2.shape[1]
+    w = weight.reshape(weight.shape[0], -1).contiguous().float()
+    Co = w.shape[0]
+    if w.shape[1] != C1 + C2:
+        raise ValueError("weight has %d input channels, inputs have %d" % (w.shape[1], C1 + C2))
+    sc, sh = scale.contiguous().float(), shift.contiguous().float()
+    if sc.numel() != Co or sh.numel() != Co:
+        raise ValueError("scale/shift must have %d elements" % Co)
+    out = torch.empty((B, Co) + tail, dtype=torch.float32, device=x1.device)
+    with torch.cuda.device(x1.device):
+        check(lib.ffb6d_fusion_mlp_fwd(x1c.data_ptr(), C1, x2c.data_ptr() if x2c is not None else None, C2,
+                                       w.data_ptr(), sc.data_ptr(), sh.data_ptr(), B, Co, P, int(bool(relu)),
+                                       out.data_ptr(), _stream(x1.device)))
+    return out
+
+
 # --------------------------------------------------------------------------- depth -> point sets
 def backproject(depth, K, choose):
     """Depth map -> the point sets of the fusion schedule, on the GPU; replaces ``dpt_2_pcld`` +

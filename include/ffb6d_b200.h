@@ -175,6 +175,21 @@ int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_i
                                     int64_t B, int64_t N, int K,
                                     float *out, ffb6d_stream_t stream);
 
+/* ---- fusion 1x1 MLP (tensor cores) ---------------------------------------- */
+/*
+ * out[b,co,p] = act( scale[co] * sum_ci W[co,ci] * cat(x1,x2)[b,ci,p] + shift[co] )
+ * Replaces torch.cat + pt_utils.Conv2d(kernel_size=(1,1), bn=True) with frozen (eval)
+ * BatchNorm statistics (models/pytorch_utils.py:75-129,168-201; built models/ffb6d.py:55-80,
+ * 104-129; applied :246-262, 282-298): scale = gamma/sqrt(var+eps), shift = beta - mean*scale.
+ * tcgen05 TF32 tensor cores with 3xTF32 operand splitting: agrees with the fp32 path to ~1e-6
+ * relative (the 1e-5 contract).  x1 [B,C1,P], x2 [B,C2,P] or NULL (C2 = 0), weight [Co,C1+C2]
+ * row-major, out [B,Co,P]; all f32, NCHW (point axis contiguous).  relu != 0 applies ReLU.
+ */
+int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C2,
+                         const float *weight, const float *scale, const float *shift,
+                         int64_t B, int64_t Co, int64_t P, int relu, float *out,
+                         ffb6d_stream_t stream);
+
 /* ---- depth map -> searched point sets ------------------------------------- */
 /*
  * Back-projection of the depth image and extraction of the four point sets the fusion
