@@ -247,6 +247,7 @@ def main():
     ap.add_argument("--layout", default="nchw", choices=["nchw", "channels_last"])
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per CPU-arm sample (0 = #cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mlp", action="store_true", help="skip the separately reported fusion-MLP timing")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA graph replays")
     ap.add_argument("--per-op", action="store_true", help="also print the per-op table to stderr")
     args = ap.parse_args()
@@ -463,6 +464,39 @@ def main():
             sys.stderr.write("%-28s %8.3f ms/step  %8.1f GB/s\n" % (
                 name, d["ms"] / steps, d["bytes"] / (d["ms"] / 1e3) / 1e9))
 
+    # ---- reported separately: the 28 fusion 1x1 MLPs on the tensor cores
+    mlp_line = None
+    if not args.no_mlp:
+        from ffb6d_b200.pipeline import FusionMLPs
+        mlps = FusionMLPs(B, n_points=N0, device=dev, seed=rank)
+        for _ in range(2):
+            mlps()
+        torch.cuda.synchronize()
+        m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = max(2, min(steps, 5))
+        m0.record()
+        for _ in range(reps):
+            mlps()
+        m1.record()
+        torch.cuda.synchronize()
+        mlp_ms = m0.elapsed_time(m1) / reps
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                bf16_peak = float(json.load(fh)["bf16_tflops"])
+        except Exception:
+            bf16_peak = 1590.0
+        tf32_tflops = 3.0 * mlps.flops / (mlp_ms / 1e3) / 1e12          # three TF32 MMAs per fp32 product
+        mlp_line = {"layers": len(mlps.layers), "ms_per_step": mlp_ms, "fp32_equiv_tflops": tf32_tflops / 3.0,
+                    "tf32_tflops_issued": tf32_tflops,
+                    "roofline": {"bound": "tensor", "achieved": tf32_tflops, "peak": bf16_peak / 2.0,
+                                 "unit": "TFLOP/s", "frac": tf32_tflops / (bf16_peak / 2.0),
+                                 "note": "kind::tf32 peak taken as half the measured bf16 peak; 3xTF32 split for "
+                                         "fp32 fidelity (1e-5 contract)"},
+                    "note": "28 fused cat+conv1x1+BN(eval)+ReLU layers of the fusion stack (models/ffb6d.py:55-80,"
+                            "104-129), frames_per_gpu x 34.1 GFLOP; not part of `value`"}
+        del mlps
+        torch.cuda.empty_cache()
+
     # ---- CPU baseline (rank 0, N=1 only): the reference's compiled ops on this box's cores
     cpu_baseline = None
     if world == 1 and not args.no_cpu_baseline:
@@ -496,7 +530,7 @@ def main():
         "instrumented_note": "eager launches + per-op events behind a %.1f ms spin kernel; the CPU needs %.1f ms to "
                              "enqueue a step" % (spin_ms / steps, enqueue_ms / steps),
         "roofline": roofline, "pass_roofline": pass_roofline,
-        "cpu_baseline": cpu_baseline, "clocks": clocks,
+        "fusion_mlps": mlp_line, "cpu_baseline": cpu_baseline, "clocks": clocks,
     }
     emit(line)
     if dist is not None:

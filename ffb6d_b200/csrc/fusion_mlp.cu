@@ -19,6 +19,10 @@
 //     point-major in memory)
 //   * two stages: the MMAs of stage s run asynchronously (completion -> mbarrier via
 //     tcgen05.commit) while the threads stage s+1
+//   * the tensor core adds into its fp32 accumulator with truncation, which drifts by ~2^-24 per
+//     MMA (measured 1.2e-5 relative at K = 2048); K is therefore accumulated in chunks of 128 into
+//     two alternating TMEM accumulators that the warps drain into round-to-nearest fp32 register
+//     sums while the next chunk is being multiplied
 //   * epilogue: tcgen05.ld 32x32b -> scale/shift/ReLU in registers -> 128-bit stores along the
 //     point axis (NCHW output, no transposition needed because M = output channel = TMEM lane).
 #include "common.cuh"
@@ -30,6 +34,7 @@ constexpr int CHUNK_BYTES = TM * 16;                  // one 16-byte K chunk of 
 constexpr int TILE_BYTES = (TK / 4) * CHUNK_BYTES;    // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
 constexpr int MLP_SMEM = 2 * STAGE_BYTES + 64;        // + barriers / tmem pointer
+constexpr int CH = 4;                                 // k-tiles per accumulation chunk (K = 128)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -85,20 +90,20 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
                   const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int relu)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE_BYTES);   // [0],[1]: stage free; [2]: all done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE_BYTES + 32);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE_BYTES);   // [0],[1]: stage free; [2],[3]: chunk done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE_BYTES + 48);
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
     const int b = blockIdx.z, m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int Ci = C1 + C2;
     const float *xb1 = x1 + (size_t)b * C1 * P;
     const float *xb2 = x2 ? x2 + (size_t)b * C2 * P : nullptr;
 
-    if (wid == 0) {   // TMEM: 128 columns of fp32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TN));
+    if (wid == 0) {   // TMEM: two accumulators of 128 fp32 columns
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(2 * TN));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 32) {
-        for (int i = 0; i < 3; ++i)
+        for (int i = 0; i < 4; ++i)
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -111,6 +116,34 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
                      ((reinterpret_cast<uintptr_t>(xb1) & 15) == 0) &&
                      (!xb2 || (reinterpret_cast<uintptr_t>(xb2) & 15) == 0);
     const int nk = (Ci + TK - 1) / TK;
+    const int q = wid & 3, half = wid >> 2;   // this thread's accumulator row = 32q + lane, columns 64*half ..
+    float acc[64];
+#pragma unroll
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    // add chunk `c`'s TMEM accumulator (round-to-nearest) into the register sums
+    auto drain = [&](int c) {
+        const int buf = c & 1;
+        mbar_wait(smem_u32(bars + 2 + buf), (uint32_t)((c >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint32_t v[32];
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + 64 * half + 32 * i);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc[32 * i + j] = __fadd_rn(acc[32 * i + j], __uint_as_float(v[j]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
     for (int kt = 0; kt < nk; ++kt) {
         const int st = kt & 1, k0 = kt * TK;
         unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
@@ -177,68 +210,53 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
 #pragma unroll
+            const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
             for (int j = 0; j < TK / 8; ++j) {   // one MMA consumes K = 8 (two 16-byte chunks)
                 const uint32_t off = j * 2 * CHUNK_BYTES;
-                umma_tf32(tmem_d, umma_desc(a_hi + off), umma_desc(b_hi + off), (kt > 0 || j > 0) ? 1u : 0u);
-                umma_tf32(tmem_d, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
-                umma_tf32(tmem_d, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
+                umma_tf32(d_buf, umma_desc(a_hi + off), umma_desc(b_hi + off), (kt % CH != 0 || j > 0) ? 1u : 0u);
+                umma_tf32(d_buf, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
+                umma_tf32(d_buf, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
             }
             // arrive on this stage's barrier when the MMAs issued so far have completed
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                          :: "r"(smem_u32(bars + st)) : "memory");
-            if (kt == nk - 1)
+            if (kt % CH == CH - 1 || kt == nk - 1)   // ... and on the chunk's barrier when a chunk ends
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             :: "r"(smem_u32(bars + 2)) : "memory");
+                             :: "r"(smem_u32(bars + 2 + ((kt / CH) & 1))) : "memory");
         }
+        // the previous chunk is drained while the tensor core works on this one
+        if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
     }
-    // ---- epilogue: TMEM -> registers -> scale/shift/ReLU -> global
-    mbar_wait(smem_u32(bars + 2), 0);
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    drain((nk - 1) / CH);
+    // ---- epilogue: register sums -> scale/shift/ReLU -> global
     {
-        const int q = wid & 3, half = wid >> 2;
         const int gm = m0 + 32 * q + lane;
-        const float sc = (gm < Co) ? __ldg(scale + gm) : 0.f, sh = (gm < Co) ? __ldg(shift + gm) : 0.f;
-        float *orow = out + ((size_t)b * Co + gm) * P;
+        if (gm < Co) {
+            const float sc = __ldg(scale + gm), sh = __ldg(shift + gm);
+            float *orow = out + ((size_t)b * Co + gm) * P;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            const int c0 = 64 * half + 32 * i;
-            uint32_t v[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)c0;
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-            if (gm < Co) {
+            for (int j = 0; j < 64; j += 4) {
+                const int gn = n0 + 64 * half + j;
+                float y[4];
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) {
-                    const int gn = n0 + c0 + j;
-                    float y[4];
+                for (int u = 0; u < 4; ++u) {
+                    // BN(eval) folded: y = conv * scale + shift, unfused like torch's affine
+                    y[u] = __fadd_rn(__fmul_rn(acc[j + u], sc), sh);
+                    if (relu) y[u] = fmaxf(y[u], 0.f);
+                }
+                if (vec && gn + 3 < P) {
+                    *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
+                } else {
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        // BN(eval) folded: y = conv * scale + shift, unfused like torch's affine
-                        y[u] = __fadd_rn(__fmul_rn(__uint_as_float(v[j + u]), sc), sh);
-                        if (relu) y[u] = fmaxf(y[u], 0.f);
-                    }
-                    if (vec && gn + 3 < P) {
-                        *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
-                    } else {
-#pragma unroll
-                        for (int u = 0; u < 4; ++u)
-                            if (gn + u < P) orow[gn + u] = y[u];
-                    }
+                    for (int u = 0; u < 4; ++u)
+                        if (gn + u < P) orow[gn + u] = y[u];
                 }
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(TN));
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(2 * TN));
 }
 
 }  // namespace ffb6d

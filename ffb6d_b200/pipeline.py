@@ -154,6 +154,33 @@ class FusionPass:
         return inputs, self.run_gathers(inputs, timer)
 
 
+class FusionMLPs:
+    """The 28 fusion 1x1 MLPs of one batch with synthetic weights and inputs (eval-mode BatchNorm
+    folded into scale/shift), run through the tensor-core kernel.  BASELINE.md reports them
+    separately from the KNN + gather pass."""
+
+    def __init__(self, batch, n_points=12288, h=480, w=640, device="cuda", seed=0):
+        self.B = batch
+        self.device = torch.device(device)
+        self.layers = S.fusion_mlp_schedule(n_points, h, w)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+        self.args = []
+        self.flops = 0
+        for name, P, C1, C2, Co in self.layers:
+            def rnd(*shape):
+                return torch.randn(shape, generator=g, device=self.device, dtype=torch.float32)
+            x1 = rnd(batch, C1, P, 1)
+            x2 = rnd(batch, C2, P, 1) if C2 else None
+            wgt = rnd(Co, C1 + C2) / float(C1 + C2) ** 0.5
+            scale = torch.rand(Co, generator=g, device=self.device) + 0.5
+            shift = rnd(Co) * 0.1
+            self.args.append((x1, x2, wgt, scale, shift))
+            self.flops += 2 * batch * Co * (C1 + C2) * P
+
+    def __call__(self):
+        return [ops.fusion_mlp(*a) for a in self.args]
+
+
 class OpTimer:
     """CUDA-event pair per op on the current stream; durations are read after a synchronize.
     Events come from a pool created up front so that recording costs the CPU as little as possible."""

@@ -83,6 +83,24 @@ def gather_schedule(n_points=12288, h=480, w=640):
     return g
 
 
+def fusion_mlp_schedule(n_points=12288, h=480, w=640):
+    """The 28 fusion 1x1 MLPs of ``FFB6D.forward`` as ``(name, P, C1, C2, Co)``: positions, the two
+    concatenated input widths (C2 = 0 for the ``*_pre`` layers) and the output width
+    (models/ffb6d.py:55-80, 104-129)."""
+    N = [set_size(("cld", i), n_points) for i in range(5)]
+    HW = {sr: set_size(("img", sr), n_points, h, w) for sr in (1, 2, 4, 8)}
+    layers = []
+    for i in range(N_DS_LAYERS):
+        cr, cp, n1, hw = DS_RGB_OC[i], DS_RNDLA_OC[i], N[i + 1], HW[RGB_DS_SR[i]]
+        layers += [("ds%d_r2p_pre" % i, n1, cr, 0, cp), ("ds%d_r2p_fuse" % i, n1, cp, cp, cp),
+                   ("ds%d_p2r_pre" % i, n1, cp, 0, cr), ("ds%d_p2r_fuse" % i, hw, cr, cr, cr)]
+    for i in range(N_UP_LAYERS):
+        cr, cp, n1, hw = UP_RGB_OC[i], UP_RNDLA_OC[i], N[N_DS_LAYERS - i - 1], HW[RGB_UP_SR[i]]
+        layers += [("up%d_r2p_pre" % i, n1, cr, 0, cp), ("up%d_r2p_fuse" % i, n1, cp, cp, cp),
+                   ("up%d_p2r_pre" % i, n1, cp, 0, cr), ("up%d_p2r_fuse" % i, hw, cr, cr, cr)]
+    return layers
+
+
 def knn_alg_bytes(S, Q, K):
     """Algorithmic HBM bytes of one KNN call: xyz in once, int32 idx out."""
     return 12 * S + 12 * Q + 4 * Q * K
