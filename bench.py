@@ -404,7 +404,7 @@ def main():
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     inst_ms, spin_ms, enqueue_ms = 0.0, 0.0, 0.0
-    spin_cycles = int(2.0e9 * 0.004 * max(4.0, ms / args.steps))   # ~4x a step: the CPU gets a head start
+    spin_cycles = int(40e6)   # ~19 ms at 2.1 GHz: the CPU enqueues a whole step (~3 ms) behind it
     for _ in range(args.steps):
         s0.record()
         torch.cuda._sleep(spin_cycles)
