@@ -38,11 +38,12 @@ constexpr int CH = 4;                                 // k-tiles per accumulatio
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// round-to-nearest (ties away) to TF32's 10-bit mantissa with two full-rate integer ops; identical to
+// cvt.rna.tf32.f32 for finite inputs (that conversion runs on the quarter-rate conversion pipe and was
+// the staging bottleneck)
 __device__ __forceinline__ float to_tf32(float x)
 {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-    return __uint_as_float(r);
+    return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
 __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo)
@@ -144,16 +145,15 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
         }
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     };
-    for (int kt = 0; kt < nk; ++kt) {
-        const int st = kt & 1, k0 = kt * TK;
-        unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
-        unsigned char *sB_hi = sA_lo + TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
-        if (kt >= 2) mbar_wait(smem_u32(bars + st), ((kt >> 1) - 1) & 1);   // MMAs that read this stage are done
-
-        // ---- A = W[m0.., k0..]: 128 rows x 8 chunks, 4 chunks per thread
+    // global -> registers: A = W[m0.., k0..] (128 rows x 8 chunks, 4 chunks per thread) and
+    // B = X[k0.., n0..] (one 4(k) x 4(n) block per thread)
+    auto load_tile = [&](int kt, float4 (&ra)[4], float4 (&rb)[4]) {
+        const int k0 = kt * TK;
+        // warp w stages K chunk w; lanes take consecutive rows so the 16-byte shared-memory stores of a
+        // warp are contiguous (bank-conflict free); W is small and L2-resident, the strided reads are cheap
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            const int f = tid + 256 * i, m = f >> 3, c = f & 7;
+            const int m = lane + 32 * i, c = wid;
             const int gm = m0 + m, gk = k0 + 4 * c;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gm < Co) {
@@ -167,49 +167,73 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
                     if (gk + 3 < Ci) v.w = __ldg(src + 3);
                 }
             }
-            float4 hi, lo;
-            split4(v, hi, lo);
+            ra[i] = v;
+        }
+        const int kg = tid >> 5, ng = tid & 31;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int gk = k0 + 4 * kg + j, gn = n0 + 4 * ng;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gk < Ci) {
+                const float *row = (gk < C1) ? xb1 + (size_t)gk * P : xb2 + (size_t)(gk - C1) * P;
+                if (vec && gn + 3 < P) {
+                    v = __ldg(reinterpret_cast<const float4 *>(row + gn));
+                } else {
+                    if (gn + 0 < P) v.x = __ldg(row + gn + 0);
+                    if (gn + 1 < P) v.y = __ldg(row + gn + 1);
+                    if (gn + 2 < P) v.z = __ldg(row + gn + 2);
+                    if (gn + 3 < P) v.w = __ldg(row + gn + 3);
+                }
+            }
+            rb[j] = v;
+        }
+    };
+    // registers -> hi/lo split -> shared memory in the UMMA K-major layout (X transposed on the way)
+    auto store_tile = [&](int st, const float4 (&ra)[4], const float4 (&rb)[4]) {
+        unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
+        unsigned char *sB_hi = sA_lo + TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
+        float4 hi, lo;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int m = lane + 32 * i, c = wid;
+            split4(ra[i], hi, lo);
             *reinterpret_cast<float4 *>(sA_hi + c * CHUNK_BYTES + m * 16) = hi;
             *reinterpret_cast<float4 *>(sA_lo + c * CHUNK_BYTES + m * 16) = lo;
         }
-        // ---- B = X[k0.., n0..] transposed to K-major: one 4(k) x 4(n) block per thread
-        {
-            const int kg = tid >> 5, ng = tid & 31;
-            float4 r[4];
+        const int kg = tid >> 5, ng = tid & 31;
+        const float4 t0 = make_float4(rb[0].x, rb[1].x, rb[2].x, rb[3].x);   // n = 4ng + 0, k = 4kg .. 4kg+3
+        const float4 t1 = make_float4(rb[0].y, rb[1].y, rb[2].y, rb[3].y);
+        const float4 t2 = make_float4(rb[0].z, rb[1].z, rb[2].z, rb[3].z);
+        const float4 t3 = make_float4(rb[0].w, rb[1].w, rb[2].w, rb[3].w);
+        unsigned char *bh = sB_hi + kg * CHUNK_BYTES + (4 * ng) * 16, *bl = sB_lo + kg * CHUNK_BYTES + (4 * ng) * 16;
+        // a lane owns four consecutive 16-byte slots (64-byte lane stride): rotating which slot each
+        // lane writes per instruction makes every quarter-warp cover all 32 banks
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int gk = k0 + 4 * kg + j, gn = n0 + 4 * ng;
-                r[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (gk < Ci) {
-                    const float *row = (gk < C1) ? xb1 + (size_t)gk * P : xb2 + (size_t)(gk - C1) * P;
-                    if (vec && gn + 3 < P) {
-                        r[j] = __ldg(reinterpret_cast<const float4 *>(row + gn));
-                    } else {
-                        if (gn + 0 < P) r[j].x = __ldg(row + gn + 0);
-                        if (gn + 1 < P) r[j].y = __ldg(row + gn + 1);
-                        if (gn + 2 < P) r[j].z = __ldg(row + gn + 2);
-                        if (gn + 3 < P) r[j].w = __ldg(row + gn + 3);
-                    }
-                }
-            }
-            const float4 t0 = make_float4(r[0].x, r[1].x, r[2].x, r[3].x);   // n = 4ng + 0, k = 4kg .. 4kg+3
-            const float4 t1 = make_float4(r[0].y, r[1].y, r[2].y, r[3].y);
-            const float4 t2 = make_float4(r[0].z, r[1].z, r[2].z, r[3].z);
-            const float4 t3 = make_float4(r[0].w, r[1].w, r[2].w, r[3].w);
-            float4 hi, lo;
-            unsigned char *bh = sB_hi + kg * CHUNK_BYTES + (4 * ng) * 16, *bl = sB_lo + kg * CHUNK_BYTES + (4 * ng) * 16;
-            split4(t0, hi, lo); *reinterpret_cast<float4 *>(bh + 0) = hi;  *reinterpret_cast<float4 *>(bl + 0) = lo;
-            split4(t1, hi, lo); *reinterpret_cast<float4 *>(bh + 16) = hi; *reinterpret_cast<float4 *>(bl + 16) = lo;
-            split4(t2, hi, lo); *reinterpret_cast<float4 *>(bh + 32) = hi; *reinterpret_cast<float4 *>(bl + 32) = lo;
-            split4(t3, hi, lo); *reinterpret_cast<float4 *>(bh + 48) = hi; *reinterpret_cast<float4 *>(bl + 48) = lo;
+        for (int i = 0; i < 4; ++i) {
+            const int x = (i + (ng >> 1)) & 3;
+            const float4 tx = (x == 0) ? t0 : (x == 1) ? t1 : (x == 2) ? t2 : t3;
+            split4(tx, hi, lo);
+            *reinterpret_cast<float4 *>(bh + 16 * x) = hi;
+            *reinterpret_cast<float4 *>(bl + 16 * x) = lo;
         }
+    };
+
+    float4 ra[4], rb[4], na[4], nb[4];
+    load_tile(0, ra, rb);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int st = kt & 1;
+        unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
+        unsigned char *sB_hi = sA_lo + TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
+        // the next tile's global loads are in flight while this one is split, stored and multiplied
+        if (kt + 1 < nk) load_tile(kt + 1, na, nb);
+        if (kt >= 2) mbar_wait(smem_u32(bars + st), ((kt >> 1) - 1) & 1);   // MMAs that read this stage are done
+        store_tile(st, ra, rb);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
         asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
         __syncthreads();
         if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
-#pragma unroll
             const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
             for (int j = 0; j < TK / 8; ++j) {   // one MMA consumes K = 8 (two 16-byte chunks)
                 const uint32_t off = j * 2 * CHUNK_BYTES;
@@ -226,6 +250,11 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
         }
         // the previous chunk is drained while the tensor core works on this one
         if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // the prefetched tile becomes the current one
+            ra[i] = na[i];
+            rb[i] = nb[i];
+        }
     }
     drain((nk - 1) / CH);
     // ---- epilogue: register sums -> scale/shift/ReLU -> global
