@@ -289,7 +289,9 @@ gather_max_ncs_klane_kernel(const float *__restrict__ feat, const IdxT *__restri
 {
     constexpr int TQ = 32;            // queries per CTA tile (one 128-byte output segment per channel)
     constexpr int QPW = 32 / KT;      // queries per warp at a time
-    constexpr int CCH = 64;           // channels per CTA pass
+    constexpr int CCH = 8;            // channels per CTA: many CTAs per frame keep ONE frame's rows in L2
+                                      // (ncu: with 64 channels per CTA twelve frames were in flight,
+                                      // 235 MB of rows thrashed the 126 MB L2 and DRAM read them twice)
     __shared__ float tile[CCH][TQ + 1];
     const int b = blockIdx.z;
     const int q_tile = blockIdx.x * TQ;
@@ -585,7 +587,7 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         FFB6D_LAUNCH_OK("gather1_ncs_direct_kernel");
     } else if ((KT == 8 || KT == 16 || KT == 32) && !getenv("FFB6D_GATHER_DIRECT")) {
         if constexpr (KT == 8 || KT == 16 || KT == 32) {
-            dim3 grid((unsigned)ceil_div(Q, 32), (unsigned)std::min<int64_t>(ceil_div(C, 64), 65535), (unsigned)B);
+            dim3 grid((unsigned)ceil_div(Q, 32), (unsigned)std::min<int64_t>(ceil_div(C, 8), 65535), (unsigned)B);
             gather_max_ncs_klane_kernel<IdxT, KT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
             FFB6D_LAUNCH_OK("gather_max_ncs_klane_kernel");
         }

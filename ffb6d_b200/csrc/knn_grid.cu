@@ -60,7 +60,7 @@ struct __align__(16) QueryState {
     int ovf_count;  // queries handed to the overflow pass (front of the ovf list)
     int dup_count;  // far queries equal to rep_q (back of the ovf list)
     int rep_q;      // 1 + first far query of this item, 0 if none
-    int pad;
+    int pad;        // CTAs of the overflow kernel that have finished (last one copies the duplicate rows)
 };
 
 // The grid of one support batch: written by knn_grid_build, read-only afterwards, so any
@@ -879,28 +879,31 @@ grid_overflow_kernel(const float *__restrict__ support, const float *__restrict_
     }
 }
 
-// ------------------------------------------------------------------ F'. overflow, one warp per query (K <= 32)
-// Same full scan, but the 32 lanes split the support and share the sorted list of
-// grid_search_warp_kernel: a handful of far queries (typically one per frame once duplicates
-// are folded) no longer costs a serial walk over the whole support by a single thread.
+// ------------------------------------------------------------------ F'. overflow + duplicate rows, one CTA per query (K <= 32)
+// Same full scan, but the eight warps of a CTA split the support, each building the lane-distributed
+// sorted list of grid_search_warp_kernel; warp 0 merges the eight lists.  A handful of far queries
+// (typically one per frame once duplicates are folded) no longer costs a serial walk over the whole
+// support.  The last CTA of a batch item to finish then copies the representative's row to the
+// queries that were equal to it (fused: no separate launch).
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 grid_overflow_warp_kernel(const float *__restrict__ support, const float *__restrict__ query, int S,
-                          int Q, int K, const QueryState *__restrict__ state_all,
-                          const int *__restrict__ ovf_all, IdxT *__restrict__ idx_out)
+                          int Q, int K, QueryState *state_all, const int *__restrict__ ovf_all,
+                          IdxT *__restrict__ idx_out)
 {
+    __shared__ key_t64 lists[8][32];
+    __shared__ int last_flag;
     const int b = blockIdx.y;
     const int count = state_all[b].ovf_count;
-    const int lane = threadIdx.x & 31;
-    const int wpb = blockDim.x >> 5;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const float *sup = support + (size_t)b * S * 3;
-    for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < count; t += gridDim.x * wpb) {
+    for (int t = blockIdx.x; t < count; t += gridDim.x) {   // CTA-uniform
         const int q = ovf_all[(size_t)b * Q + t];
         const float *qp = query + ((size_t)b * Q + q) * 3;
         const float qx = __ldg(qp), qy = __ldg(qp + 1), qz = __ldg(qp + 2);
         key_t64 mine = KEY_EMPTY;
         bool list_empty = true;
-        for (int s0 = 0; s0 < S; s0 += 32) {
+        for (int s0 = wid * 32; s0 < S; s0 += 8 * 32) {
             const int sI = s0 + lane;
             key_t64 cand = KEY_INVALID;
             if (sI < S)
@@ -908,7 +911,29 @@ grid_overflow_warp_kernel(const float *__restrict__ support, const float *__rest
                                            __ldg(sup + (size_t)sI * 3 + 2)), sI);
             warp_list_offer(mine, cand, K, lane, list_empty);
         }
-        if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)(unsigned)(mine & 0xffffffffu);
+        lists[wid][lane] = mine;
+        __syncthreads();
+        if (wid == 0) {
+            list_empty = false;
+            for (int w = 1; w < 8; ++w) warp_list_offer(mine, lists[w][lane], K, lane, list_empty);
+            if (lane < K) idx_out[((size_t)b * Q + q) * K + lane] = (IdxT)(unsigned)(mine & 0xffffffffu);
+        }
+        __syncthreads();
+    }
+    // ---- rows of the queries equal to the representative far query: done by the last CTA of this item
+    const int dups = state_all[b].dup_count;
+    if (dups == 0) return;   // CTA-uniform
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) last_flag = (atomicAdd(&state_all[b].pad, 1) == (int)gridDim.x - 1);
+    __syncthreads();
+    if (!last_flag) return;
+    __threadfence();
+    const int rep = state_all[b].rep_q - 1;
+    const IdxT *src = idx_out + ((size_t)b * Q + rep) * K;
+    for (int t = threadIdx.x; t < dups * K; t += blockDim.x) {
+        const int q = ovf_all[(size_t)b * Q + (Q - 1 - t / K)];
+        idx_out[((size_t)b * Q + q) * K + t % K] = __ldcg(src + t % K);
     }
 }
 
@@ -979,19 +1004,20 @@ static int launch_search(const float *support, const float *query, int64_t B, in
     FFB6D_LAUNCH_OK("grid_search_kernel");
     const int64_t per_item = std::max<int64_t>(1, 4 * kNumSMs / B);
     if (K <= 32) {
-        dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, 8), per_item), (unsigned)B);
+        dim3 ogrid((unsigned)std::min<int64_t>(Q, per_item), (unsigned)B);
         grid_overflow_warp_kernel<IdxT><<<ogrid, 256, 0, st>>>(support, query, (int)S, (int)Q, K, qs.state,
                                                                qs.ovf, (IdxT *)idx_out);
+        FFB6D_LAUNCH_OK("grid_overflow_warp_kernel");
     } else {
         constexpr int OT = (KCAP >= 32) ? 64 : 128;
         dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, OT), per_item), (unsigned)B);
         grid_overflow_kernel<KCAP, OT, 1024, IdxT><<<ogrid, OT, 0, st>>>(
             support, query, (int)S, (int)Q, K, qs.state, qs.ovf, (IdxT *)idx_out);
+        FFB6D_LAUNCH_OK("grid_overflow_kernel");
+        dim3 dgrid((unsigned)std::min<int64_t>(ceil_div(Q * K, 256), per_item), (unsigned)B);
+        grid_dup_copy_kernel<IdxT><<<dgrid, 256, 0, st>>>((int)Q, K, qs.state, qs.ovf, (IdxT *)idx_out);
+        FFB6D_LAUNCH_OK("grid_dup_copy_kernel");
     }
-    FFB6D_LAUNCH_OK("grid_overflow_kernel");
-    dim3 dgrid((unsigned)std::min<int64_t>(ceil_div(Q * K, 256), per_item), (unsigned)B);
-    grid_dup_copy_kernel<IdxT><<<dgrid, 256, 0, st>>>((int)Q, K, qs.state, qs.ovf, (IdxT *)idx_out);
-    FFB6D_LAUNCH_OK("grid_dup_copy_kernel");
     return FFB6D_OK;
 }
 

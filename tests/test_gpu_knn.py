@@ -176,3 +176,39 @@ def test_knn_grid_build_once_query_many(cuda):
         assert np.array_equal(got, O.knn_search(sup, q, k)), (q.shape, k)
     got = grid.query(ts, 16, out_dtype=torch.int64).cpu().numpy()              # self search
     assert np.array_equal(got, O.knn_search(sup, sup, 16))
+
+
+@pytest.mark.parametrize("n_points,k", [(4096, 8), (4096, 32), (40960, 16), (40960, 8), (131072, 32), (131072, 16)])
+def test_stress_sweep_sizes(cuda, n_points, k):
+    """BASELINE configs[4]: N in {4096 .. 131072}, K in {8,16,32} on one frame: every index tensor of
+    the schedule is checked on sampled rows against the oracle, plus ordering / self-first properties."""
+    from ffb6d_b200.synthetic import make_frame
+    from ffb6d_b200.schedule import knn_schedule
+    fr = make_frame(31, n_points=n_points)
+    cld = torch.from_numpy(fr["cld"])[None].cuda()
+    xyz = torch.from_numpy(fr["dpt_xyz"])[None].cuda()
+    inputs = F.build_ffb6d_indices(cld, xyz, k=k)
+    ps = frame_point_sets(fr, n_points)
+    rs = np.random.RandomState(1)
+    for key, s, q, kk in knn_schedule(n_points, k=k):
+        idx = inputs[key][0].cpu().numpy()
+        S, Q = len(ps[s]), len(ps[q])
+        assert idx.shape == (Q, kk) and idx.min() >= 0 and idx.max() < S, key
+        rows = rs.choice(Q, size=min(Q, 48), replace=False)
+        want = O.knn_search(ps[s][None], ps[q][None][:, rows], kk)[0]
+        ok, _, _, msg = O.knn_matches(ps[s][None], ps[q][None][:, rows], idx[None][:, rows], want[None])
+        assert ok, "%s: %s" % (key, msg)
+        if s == q:
+            assert (idx[:, 0] == np.arange(Q)).all(), key
+
+
+@pytest.mark.parametrize("k", [2, 31, 32, 33, 64])
+def test_knn_all_k_paths(cuda, k):
+    """warp-per-query (K <= 32) and thread-per-query (K > 32) searches, overflow paths included."""
+    rs = np.random.RandomState(k)
+    sup = (rs.rand(2, 6000, 3) * np.array([1.0, 1.0, 0.05])).astype(np.float32)
+    qry = np.concatenate([rs.rand(2, 500, 3).astype(np.float32), rs.rand(2, 40, 3).astype(np.float32) + 5.0], 1)
+    qry[:, 520:530] = 0.0
+    for algo in (2, 1):
+        got = gpu_knn(sup, qry, k, algo)
+        assert np.array_equal(got, O.knn_search(sup, qry, k)), (k, algo)
