@@ -88,7 +88,8 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 __global__ void __launch_bounds__(256, 1)
 fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
                   const float *__restrict__ w, const float *__restrict__ scale,
-                  const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int relu)
+                  const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
+                  float slope)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE_BYTES);   // [0],[1]: stage free; [2],[3]: chunk done
@@ -113,9 +114,11 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    const bool vec = ((P & 3) == 0) && ((Ci & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(xb1) & 15) == 0) &&
-                     (!xb2 || (reinterpret_cast<uintptr_t>(xb2) & 15) == 0);
+    // 128-bit paths: weights need Ci % 4 == 0, activations / outputs need P % 4 == 0 (and aligned bases)
+    const bool vecA = ((Ci & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
+    const bool vec = ((P & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb1) & 15) == 0) &&
+                     (!xb2 || (reinterpret_cast<uintptr_t>(xb2) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
     const int nk = (Ci + TK - 1) / TK;
     const int q = wid & 3, half = wid >> 2;   // this thread's accumulator row = 32q + lane, columns 64*half ..
     float acc[64];
@@ -158,7 +161,7 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gm < Co) {
                 const float *src = w + (size_t)gm * Ci + gk;
-                if (vec && gk + 3 < Ci) {
+                if (vecA && gk + 3 < Ci) {
                     v = __ldg(reinterpret_cast<const float4 *>(src));
                 } else {
                     if (gk + 0 < Ci) v.x = __ldg(src + 0);
@@ -271,7 +274,8 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
                 for (int u = 0; u < 4; ++u) {
                     // BN(eval) folded: y = conv * scale + shift, unfused like torch's affine
                     y[u] = __fadd_rn(__fmul_rn(acc[j + u], sc), sh);
-                    if (relu) y[u] = fmaxf(y[u], 0.f);
+                    if (act == 1) y[u] = fmaxf(y[u], 0.f);
+                    else if (act == 2) y[u] = (y[u] > 0.f) ? y[u] : __fmul_rn(y[u], slope);   // LeakyReLU
                 }
                 if (vec && gn + 3 < P) {
                     *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
@@ -294,9 +298,10 @@ using namespace ffb6d;
 
 extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C2, const float *weight,
                                     const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
-                                    int relu, float *out, ffb6d_stream_t stream)
+                                    int act, float negative_slope, float *out, ffb6d_stream_t stream)
 {
     FFB6D_CHECK_ARG(B >= 0 && C1 >= 1 && C2 >= 0 && Co >= 1 && P >= 0, "fusion_mlp_fwd: bad size");
+    FFB6D_CHECK_ARG(act >= 0 && act <= 2, "fusion_mlp_fwd: act=%d (0 none, 1 ReLU, 2 LeakyReLU)", act);
     FFB6D_CHECK_ARG(B < 65536 && Co <= 65535ll * TM && P < (1ll << 31) && C1 + C2 < (1ll << 31),
                     "fusion_mlp_fwd: size too large");
     if (B == 0 || P == 0) return FFB6D_OK;
@@ -308,7 +313,7 @@ extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2
     }
     dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
     fusion_mlp_kernel<<<grid, 256, MLP_SMEM, (cudaStream_t)stream>>>(x1, (int)C1, C2 ? x2 : nullptr, (int)C2, weight,
-                                                                    scale, shift, out, (int)Co, (int)P, relu);
+                                                                    scale, shift, out, (int)Co, (int)P, act, negative_slope);
     FFB6D_LAUNCH_OK("fusion_mlp_kernel");
     return FFB6D_OK;
 }

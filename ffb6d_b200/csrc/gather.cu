@@ -511,6 +511,98 @@ rel_pos_enc_kernel(const float *__restrict__ xyz, const IdxT *__restrict__ idx,
     o[9] = nz;
 }
 
+// channel-major variant: out[b, j, n, k], j = 0..9 (coalesced along k/n per channel plane)
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+rel_pos_enc_cm_kernel(const float *__restrict__ xyz, const IdxT *__restrict__ idx,
+                      float *__restrict__ out, int N, int K, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;  // (b*N+n)*K+k
+    if (t >= total) return;
+    const long long bn = t / K;
+    const int b = (int)(bn / N);
+    const long long plane = (long long)N * K;
+    const long long within = t - (long long)b * plane;   // n*K + k
+    const int j = (int)__ldg(idx + t);
+    const float *pc = xyz + (size_t)bn * 3;
+    const float *pn = xyz + ((size_t)b * N + j) * 3;
+    const float cx = __ldg(pc), cy = __ldg(pc + 1), cz = __ldg(pc + 2);
+    const float nx = __ldg(pn), ny = __ldg(pn + 1), nz = __ldg(pn + 2);
+    const float dx = __fsub_rn(cx, nx), dy = __fsub_rn(cy, ny), dz = __fsub_rn(cz, nz);
+    const float ss = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    float *o = out + (size_t)b * 10 * plane + within;
+    o[0 * plane] = __fsqrt_rn(ss);
+    o[1 * plane] = dx;
+    o[2 * plane] = dy;
+    o[3 * plane] = dz;
+    o[4 * plane] = cx;
+    o[5 * plane] = cy;
+    o[6 * plane] = cz;
+    o[7 * plane] = nx;
+    o[8 * plane] = ny;
+    o[9 * plane] = nz;
+}
+
+// ------------------------------------------------------------------ attentive pooling core
+// out[b,c,n] = sum_k f[b,c,n,k] * softmax_k(att[b,c,n,:])[k]   (models/RandLA/RandLANet.py:245-248:
+// softmax(dim=3) -> mul -> sum(dim=3)); one thread per (b,c,n), the K values of f and att are
+// contiguous (two coalesced 4K-byte reads).  softmax as torch computes it: exp(x - max) / sum.
+template <int KT>
+__global__ void __launch_bounds__(256)
+att_pool_kernel(const float *__restrict__ f1, int C1, const float *__restrict__ f2, int C2,
+                const float *__restrict__ att, int N, int K, float *__restrict__ out, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // (b*C + c)*N + n
+    if (t >= total) return;
+    const int C = C1 + C2;
+    const int n = (int)(t % N);
+    const int c = (int)((t / N) % C);
+    const int b = (int)(t / ((long long)N * C));
+    const float *fp = (c < C1) ? f1 + (((size_t)b * C1 + c) * N + n) * K
+                               : f2 + (((size_t)b * C2 + (c - C1)) * N + n) * K;
+    const float *ap = att + (size_t)t * K;
+    float fv[KT > 0 ? KT : 1], av[KT > 0 ? KT : 1];
+    if constexpr (KT > 0) {
+        if ((KT % 4 == 0) && ((reinterpret_cast<uintptr_t>(fp) & 15) == 0) && ((reinterpret_cast<uintptr_t>(ap) & 15) == 0)) {
+#pragma unroll
+            for (int k = 0; k < KT / 4; ++k) {
+                const float4 u = __ldg(reinterpret_cast<const float4 *>(fp) + k);
+                const float4 v = __ldg(reinterpret_cast<const float4 *>(ap) + k);
+                fv[4 * k] = u.x; fv[4 * k + 1] = u.y; fv[4 * k + 2] = u.z; fv[4 * k + 3] = u.w;
+                av[4 * k] = v.x; av[4 * k + 1] = v.y; av[4 * k + 2] = v.z; av[4 * k + 3] = v.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < KT; ++k) {
+                fv[k] = __ldg(fp + k);
+                av[k] = __ldg(ap + k);
+            }
+        }
+        float m = av[0];
+#pragma unroll
+        for (int k = 1; k < KT; ++k) m = fmaxf(m, av[k]);
+        float den = 0.f, num = 0.f;
+        // torch: scores = exp(a - m) / sum; f_agg = sum_k f * scores  -> same operation order
+        float e[KT];
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            e[k] = expf(av[k] - m);
+            den += e[k];
+        }
+#pragma unroll
+        for (int k = 0; k < KT; ++k) num += fv[k] * (e[k] / den);
+        out[t] = num;
+    } else {
+        float m = __ldg(ap);
+        for (int k = 1; k < K; ++k) m = fmaxf(m, __ldg(ap + k));
+        float den = 0.f;
+        for (int k = 0; k < K; ++k) den += expf(__ldg(ap + k) - m);
+        float num = 0.f;
+        for (int k = 0; k < K; ++k) num += __ldg(fp + k) * (expf(__ldg(ap + k) - m) / den);
+        out[t] = num;
+    }
+}
+
 // ------------------------------------------------------------------ host-side launch logic
 static int g_max_smem_optin = -1;
 static int max_smem_optin()
@@ -536,7 +628,10 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
     // rows that fit shared memory twice over (two CTAs per SM hide the staging latency)
     const size_t budget = (size_t)smem_cap / 2;
     const int64_t want = 4 * kNumSMs;   // CTAs to aim for
-    if (row_bytes <= budget) {
+    // few queries against long rows (Q*K gathered elements << S): staging whole rows would read far
+    // more than the ~5 sectors a query's K adjacent neighbours touch per row -> K-lane gather instead
+    const bool sparse_queries = (KT == 8 || KT == 16 || KT == 32) && Q * 40 < S && !getenv("FFB6D_GATHER_DIRECT");
+    if (row_bytes <= budget && !sparse_queries) {
         int CC = (int)(budget / row_bytes);
         if (CC > C) CC = (int)C;
         // the K indices of a query are re-read once per channel chunk: keep chunks wide when K
@@ -654,7 +749,8 @@ const char *ffb6d_gather_kernel_name(int64_t B, int64_t C, int64_t S, int64_t Q,
     const bool fits = (size_t)S * sizeof(float) <= budget;
     if (K == 1) return fits ? ((Q % 4 == 0) ? "gather1_ncs_staged_v4_kernel" : "gather_max_ncs_staged_kernel")
                             : "gather1_ncs_direct_kernel";
-    if (fits) return "gather_max_ncs_staged_kernel";
+    const bool sparse_queries = (K == 8 || K == 16 || K == 32) && Q * 40 < S && !getenv("FFB6D_GATHER_DIRECT");
+    if (fits && !sparse_queries) return "gather_max_ncs_staged_kernel";
     if ((K == 8 || K == 16 || K == 32) && !getenv("FFB6D_GATHER_DIRECT")) return "gather_max_ncs_klane_kernel";
     return "gather_max_ncs_direct_kernel";
 }
@@ -786,6 +882,45 @@ int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_i
     else
         rel_pos_enc_kernel<int><<<blocks, 256, 0, st>>>(xyz, (const int *)idx, out, (int)N, K, total);
     FFB6D_LAUNCH_OK("rel_pos_enc_kernel");
+    return FFB6D_OK;
+}
+
+int ffb6d_relative_pos_encoding_cm_fwd(const float *xyz, const void *idx, int idx_is_i64, int64_t B,
+                                       int64_t N, int K, float *out, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && N >= 0 && K >= 0, "relative_pos_encoding_cm_fwd: negative size");
+    if (B == 0 || N == 0 || K == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(xyz && idx && out, "relative_pos_encoding_cm_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)B * N * K;
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    if (idx_is_i64)
+        rel_pos_enc_cm_kernel<long long><<<blocks, 256, 0, st>>>(xyz, (const long long *)idx, out, (int)N, K, total);
+    else
+        rel_pos_enc_cm_kernel<int><<<blocks, 256, 0, st>>>(xyz, (const int *)idx, out, (int)N, K, total);
+    FFB6D_LAUNCH_OK("rel_pos_enc_cm_kernel");
+    return FFB6D_OK;
+}
+
+int ffb6d_att_pool_fwd(const float *f1, int64_t C1, const float *f2, int64_t C2, const float *att, int64_t B,
+                       int64_t N, int K, float *out, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && C1 >= 1 && C2 >= 0 && N >= 0, "att_pool_fwd: bad size");
+    FFB6D_CHECK_ARG(K >= 1 && K <= FFB6D_MAX_K, "att_pool_fwd: K=%d outside [1,%d]", K, FFB6D_MAX_K);
+    if (B == 0 || N == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(f1 && att && out && (C2 == 0 || f2), "att_pool_fwd: null pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    const long long total = (long long)B * (C1 + C2) * N;
+    const unsigned blocks = (unsigned)ceil_div(total, 256);
+    if (K == 16)
+        att_pool_kernel<16><<<blocks, 256, 0, st>>>(f1, (int)C1, f2, (int)C2, att, (int)N, K, out, total);
+    else if (K == 8)
+        att_pool_kernel<8><<<blocks, 256, 0, st>>>(f1, (int)C1, f2, (int)C2, att, (int)N, K, out, total);
+    else if (K == 32)
+        att_pool_kernel<32><<<blocks, 256, 0, st>>>(f1, (int)C1, f2, (int)C2, att, (int)N, K, out, total);
+    else
+        att_pool_kernel<0><<<blocks, 256, 0, st>>>(f1, (int)C1, f2, (int)C2, att, (int)N, K, out, total);
+    FFB6D_LAUNCH_OK("att_pool_kernel");
     return FFB6D_OK;
 }
 

@@ -304,12 +304,13 @@ def gather_neighbour(pc, neighbor_idx):
     return _GatherNeighbour.apply(pc, neighbor_idx)
 
 
-def relative_pos_encoding(xyz, neigh_idx):
+def relative_pos_encoding(xyz, neigh_idx, channel_major=False):
     """10-channel relative position encoding; mirrors
     ``Building_block.relative_pos_encoding`` (models/RandLA/RandLANet.py:216-223).
     Forward only (its inputs are coordinates and indices, neither requires grad in FFB6D).
 
     :param xyz: [B, N, 3]; :param neigh_idx: [B, N, K]; :return: [B, N, K, 10]
+      (``channel_major=True``: [B, 10, N, K])
     """
     _need_cuda(xyz, "xyz")
     _need_cuda(neigh_idx, "neigh_idx")
@@ -319,6 +320,12 @@ def relative_pos_encoding(xyz, neigh_idx):
         raise ValueError("relative_pos_encoding expects xyz [B,N,3] and idx [B,N,K]")
     B, N, _ = xyz.shape
     K = idx_c.shape[2]
+    if channel_major:    # [B,10,N,K]: what .permute((0,3,1,2)).contiguous() gives (RandLANet.py:197-198)
+        out = torch.empty((B, 10, N, K), dtype=torch.float32, device=xyz.device)
+        with torch.cuda.device(xyz.device):
+            check(lib.ffb6d_relative_pos_encoding_cm_fwd(xyz.data_ptr(), idx_c.data_ptr(), i64, B, N, K,
+                                                         out.data_ptr(), _stream(xyz.device)))
+        return out
     out = torch.empty((B, N, K, 10), dtype=torch.float32, device=xyz.device)
     with torch.cuda.device(xyz.device):
         check(lib.ffb6d_relative_pos_encoding_fwd(xyz.data_ptr(), idx_c.data_ptr(), i64, B, N, K,
@@ -337,7 +344,7 @@ def fold_batchnorm(bn):
     return scale.contiguous(), (beta - mean * scale).contiguous()
 
 
-def fusion_mlp(x1, x2, weight, scale, shift, relu=True):
+def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
     """``relu(scale * conv1x1(cat(x1, x2, dim=1)) + shift)`` in one tensor-core kernel
     (``ffb6d_fusion_mlp_fwd``): the fusion layers of FFB6D (models/ffb6d.py:55-80, 104-129 applied
     at :246-262, 282-298: ``torch.cat`` -> ``pt_utils.Conv2d(1x1, bias=False)`` -> BatchNorm -> ReLU)
@@ -348,6 +355,8 @@ def fusion_mlp(x1, x2, weight, scale, shift, relu=True):
     :param weight: ``[Co, C1+C2]`` or ``[Co, C1+C2, 1, 1]`` (``conv.weight``)
     :param scale, shift: ``[Co]`` folded BatchNorm (:func:`fold_batchnorm`); pass ones / the conv
       bias for a layer without BatchNorm
+    :param relu: apply ReLU; with ``negative_slope`` given, LeakyReLU(negative_slope) instead (RandLA's
+      ``pt_utils.Conv2d``, models/RandLA/pytorch_utils.py:163-197)
     :return: ``[B, Co, ...]`` with the trailing shape of ``x1``
     """
     _need_cuda(x1, "x1")
@@ -375,8 +384,33 @@ def fusion_mlp(x1, x2, weight, scale, shift, relu=True):
     out = torch.empty((B, Co) + tail, dtype=torch.float32, device=x1.device)
     with torch.cuda.device(x1.device):
         check(lib.ffb6d_fusion_mlp_fwd(x1c.data_ptr(), C1, x2c.data_ptr() if x2c is not None else None, C2,
-                                       w.data_ptr(), sc.data_ptr(), sh.data_ptr(), B, Co, P, int(bool(relu)),
-                                       out.data_ptr(), _stream(x1.device)))
+                                       w.data_ptr(), sc.data_ptr(), sh.data_ptr(), B, Co, P,
+                                       2 if negative_slope is not None else int(bool(relu)),
+                                       float(negative_slope or 0.0), out.data_ptr(), _stream(x1.device)))
+    return out
+
+
+def att_pool(f1, f2, att):
+    """Attentive-pooling core of RandLA's ``Att_pooling`` (models/RandLA/RandLANet.py:245-248):
+    ``sum_k cat(f1, f2) * softmax(att, dim=3)`` over the neighbour axis.
+
+    :param f1: ``[B, C1, N, K]`` float32 CUDA; :param f2: ``[B, C2, N, K]`` or None
+    :param att: ``[B, C1+C2, N, K]`` attention activations (output of the layer's ``fc``)
+    :return: ``[B, C1+C2, N, 1]``
+    """
+    _need_cuda(f1, "f1")
+    _need_cuda(att, "att")
+    f1c = f1.contiguous()
+    f2c = f2.contiguous() if f2 is not None else None
+    B, C1, N, K = f1c.shape
+    C2 = f2c.shape[1] if f2c is not None else 0
+    a = att.contiguous()
+    if tuple(a.shape) != (B, C1 + C2, N, K) or f1c.dtype != torch.float32 or a.dtype != torch.float32:
+        raise ValueError("att must be float32 [B,C1+C2,N,K] matching f1/f2")
+    out = torch.empty((B, C1 + C2, N, 1), dtype=torch.float32, device=f1.device)
+    with torch.cuda.device(f1.device):
+        check(lib.ffb6d_att_pool_fwd(f1c.data_ptr(), C1, f2c.data_ptr() if f2c is not None else None, C2,
+                                     a.data_ptr(), B, N, K, out.data_ptr(), _stream(f1.device)))
     return out
 
 

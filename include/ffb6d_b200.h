@@ -174,6 +174,11 @@ int ffb6d_gather_neighbour_bwd(const float *grad_out, const void *idx, int idx_i
 int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_is_i64,
                                     int64_t B, int64_t N, int K,
                                     float *out, ffb6d_stream_t stream);
+/* Same values written channel-major, out [B,10,N,K] -- what the reference obtains with
+ * .permute((0,3,1,2)).contiguous() before the first LFA conv (RandLANet.py:197-198). */
+int ffb6d_relative_pos_encoding_cm_fwd(const float *xyz, const void *idx, int idx_is_i64,
+                                       int64_t B, int64_t N, int K,
+                                       float *out, ffb6d_stream_t stream);
 
 /* ---- fusion 1x1 MLP (tensor cores) ---------------------------------------- */
 /*
@@ -183,12 +188,23 @@ int ffb6d_relative_pos_encoding_fwd(const float *xyz, const void *idx, int idx_i
  * 104-129; applied :246-262, 282-298): scale = gamma/sqrt(var+eps), shift = beta - mean*scale.
  * tcgen05 TF32 tensor cores with 3xTF32 operand splitting: agrees with the fp32 path to ~1e-6
  * relative (the 1e-5 contract).  x1 [B,C1,P], x2 [B,C2,P] or NULL (C2 = 0), weight [Co,C1+C2]
- * row-major, out [B,Co,P]; all f32, NCHW (point axis contiguous).  relu != 0 applies ReLU.
+ * row-major, out [B,Co,P]; all f32, NCHW (point axis contiguous).
+ * act: 0 none, 1 ReLU (the fusion layers), 2 LeakyReLU(negative_slope) (RandLA's pt_utils.Conv2d,
+ * models/RandLA/pytorch_utils.py:163-197: conv -> BN(eps 1e-6) -> LeakyReLU(0.2)).
  */
 int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C2,
                          const float *weight, const float *scale, const float *shift,
-                         int64_t B, int64_t Co, int64_t P, int relu, float *out,
-                         ffb6d_stream_t stream);
+                         int64_t B, int64_t Co, int64_t P, int act, float negative_slope,
+                         float *out, ffb6d_stream_t stream);
+
+/*
+ * Attentive pooling core of RandLA's Att_pooling (models/RandLA/RandLANet.py:243-248):
+ *   out[b,c,n] = sum_k f[b,c,n,k] * softmax_k(att[b,c,n,:])[k],   f = cat(f1, f2) along channels
+ *   f1 [B,C1,N,K], f2 [B,C2,N,K] or NULL, att [B,C1+C2,N,K] -> out [B,C1+C2,N]   (f32, K <= 64)
+ * (the scores `att` come from the layer's fc = 1x1 conv, i.e. ffb6d_fusion_mlp_fwd with act 0).
+ */
+int ffb6d_att_pool_fwd(const float *f1, int64_t C1, const float *f2, int64_t C2, const float *att,
+                       int64_t B, int64_t N, int K, float *out, ffb6d_stream_t stream);
 
 /* ---- depth map -> searched point sets ------------------------------------- */
 /*

@@ -188,6 +188,53 @@ def backproject_digest():
     return out
 
 
+def lfa_cases():
+    """RandLA Dilated_res_block (mlp1 -> Building_block -> mlp2 + shortcut -> leaky_relu; Att_pooling
+    inside) executed from the reference's own class source (models/RandLA/RandLANet.py:170-250) with the
+    reference's pt_utils (models/RandLA/pytorch_utils.py), eval mode, random BN statistics."""
+    import ast
+    import importlib.util
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+    rdir = os.path.join(R.REF_ROOT, "ffb6d", "models", "RandLA")
+    spec = importlib.util.spec_from_file_location("ref_randla_pt_utils", os.path.join(rdir, "pytorch_utils.py"))
+    pt_utils = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pt_utils)
+    path = os.path.join(rdir, "RandLANet.py")
+    tree = ast.parse(open(path).read())
+    ns = {"torch": torch, "nn": nn, "F": Fn, "pt_utils": pt_utils}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ("Dilated_res_block", "Building_block", "Att_pooling"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    cases = {}
+    for name, (d_in, d_out, B, N, K, seed) in {"blk_8_16": (8, 16, 2, 96, 16, 0),
+                                               "blk_32_32": (32, 32, 1, 40, 16, 1)}.items():
+        torch.manual_seed(seed)
+        blk = ns["Dilated_res_block"](d_in, d_out)
+        g = torch.Generator().manual_seed(100 + seed)
+        with torch.no_grad():
+            for m in blk.modules():
+                if isinstance(m, nn.BatchNorm2d):
+                    m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                    m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                    m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+                    m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.3)
+        blk.eval()
+        feature = torch.randn(B, d_in, N, 1, generator=g)
+        xyz = torch.randn(B, N, 3, generator=g)
+        idx = torch.randint(0, N, (B, N, K), generator=g)
+        with torch.no_grad():
+            out = blk(feature, xyz, idx)
+            f_pc = blk.mlp1(feature)
+            lfa = blk.lfa(xyz, f_pc, idx)
+        cases.update({name + "/feature": feature.numpy(), name + "/xyz": xyz.numpy(), name + "/idx": idx.numpy(),
+                      name + "/out": out.numpy(), name + "/lfa_out": lfa.numpy(), name + "/mlp1_out": f_pc.numpy()})
+        for k, v in blk.state_dict().items():
+            if v.dtype.is_floating_point:
+                cases[name + "/sd." + k] = v.numpy()
+    return cases
+
+
 def main():
     if not R.reference_sources_present():
         raise SystemExit("needs /root/reference")
@@ -195,6 +242,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "knn_cases.npz"), **knn_cases())
     np.savez_compressed(os.path.join(OUT, "gather_cases.npz"), **gather_cases())
     np.savez_compressed(os.path.join(OUT, "grid_cases.npz"), **grid_cases())
+    np.savez_compressed(os.path.join(OUT, "lfa_cases.npz"), **lfa_cases())
     dig = {"generator": "ffb6d_b200.synthetic.make_frame", "frames": {}}
     for seed, n in ((0, 12288), (1, 12288), (2, 3072)):
         dig["frames"]["seed%d_n%d" % (seed, n)] = {"seed": seed, "n_points": n,
