@@ -212,3 +212,22 @@ def test_knn_all_k_paths(cuda, k):
     for algo in (2, 1):
         got = gpu_knn(sup, qry, k, algo)
         assert np.array_equal(got, O.knn_search(sup, qry, k)), (k, algo)
+
+
+def test_bench_cli_small(cuda):
+    """bench.py end to end on a tiny configuration: one JSON line with the contract's keys."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--batch", "2", "--n-points", "3072",
+                          "--steps", "3", "--warmup", "3", "--no-cpu-baseline", "--no-mlp"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stderr[-3000:]
+    lines = [ln for ln in out.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1, out.stdout[-2000:]
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "clocks"):
+        assert key in d, key
+    assert d["value"] > 0 and d["gpu_launches"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0
+    assert 0 < d["roofline"]["frac"] and d["roofline"]["bound"] == "hbm"

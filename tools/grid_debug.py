@@ -23,13 +23,8 @@ cho = torch.from_numpy(batch["choose"]).to(dev)
 p = FusionPass(B, device=dev)
 p.build_indices(cld, xyz, cho)
 torch.cuda.synchronize()
-names = [c for c in knn_schedule()]
-grid_calls = [w for w in ops._debug_ws if w[4] is not None]
 print("%-18s %6s %6s %3s | %9s %4s %4s %4s %8s %7s %6s %5s" % (
     "call", "S", "Q", "K", "h", "nx", "ny", "nz", "ncells", "pts/occ", "ovf", "dup"))
-gi = 0
-for key, s, q, k in names:
-    rec = next((w for w in ops._debug_ws if False), None)
 for (Bc, S, Q, K, ws), in [(w,) for w in ops._debug_ws]:
     if ws is None:
         print("%-18s %6d %6d %3d | tiled scan" % ("", S, Q, K))
