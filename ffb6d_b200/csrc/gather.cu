@@ -63,6 +63,40 @@ __device__ __forceinline__ void load_ids(const IdxT *__restrict__ ip, int K, int
     }
 }
 
+// ------------------------------------------------------------------ row staging with the bulk-copy engine
+// Copies `bytes` (multiple of 16, both sides 16-byte aligned) from global to shared memory with
+// cp.async.bulk (the 1-D TMA path, SASS UBLKCP): one thread programs the copies, the data never passes
+// through registers, and completion is signalled on an mbarrier every thread then waits on.  Deep
+// memory-level parallelism for free: a CTA has its whole 100 KB of rows in flight at once.
+__device__ __forceinline__ void stage_rows_bulk(float *smem_dst, const float *gmem_src, unsigned bytes,
+                                                unsigned long long *bar)
+{
+    const unsigned bar_a = (unsigned)__cvta_generic_to_shared(bar);
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar_a));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_a), "r"(bytes) : "memory");
+        const unsigned dst = (unsigned)__cvta_generic_to_shared(smem_dst);
+        for (unsigned off = 0; off < bytes; off += 32768u) {
+            const unsigned n = min(32768u, bytes - off);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(dst + off), "l"(reinterpret_cast<const char *>(gmem_src) + off), "r"(n), "r"(bar_a)
+                         : "memory");
+        }
+    }
+    unsigned done = 0;
+    for (int spin = 0; !done; ++spin) {
+        asm volatile(
+            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, P1;\n\t}\n"
+            : "=r"(done) : "r"(bar_a), "r"(0u) : "memory");
+        if (spin > (1 << 26)) __trap();   // never hang the GPU on a protocol bug
+    }
+}
+
 // ------------------------------------------------------------------ NCS staged
 template <typename IdxT, int KT>
 __global__ void __launch_bounds__(256)
@@ -71,19 +105,18 @@ gather_max_ncs_staged_kernel(const float *__restrict__ feat, const IdxT *__restr
                              int q_per_cta)
 {
     extern __shared__ __align__(16) float rows[];  // [cc][S]
+    __shared__ __align__(8) unsigned long long bar[1];
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * CC;
     const int cc = min(CC, C - c0);
     const float *src = feat + ((size_t)b * C + c0) * S;
     const int n = cc * S;
     if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        float4 *d4 = reinterpret_cast<float4 *>(rows);
-        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
+        stage_rows_bulk(rows, src, (unsigned)n * 4u, bar);   // whole rows in flight, no register pass
     } else {
         for (int t = threadIdx.x; t < n; t += blockDim.x) rows[t] = __ldg(src + t);
+        __syncthreads();
     }
-    __syncthreads();
 
     const int q0 = blockIdx.x * q_per_cta;
     const int q1 = min(Q, q0 + q_per_cta);
@@ -122,19 +155,18 @@ gather1_ncs_staged_v4_kernel(const float *__restrict__ feat, const IdxT *__restr
                              float *__restrict__ out, int C, int S, int Q, int CC, int q_per_cta)
 {
     extern __shared__ __align__(16) float rows[];  // [cc][S]
+    __shared__ __align__(8) unsigned long long bar[1];
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * CC;
     const int cc = min(CC, C - c0);
     const float *src = feat + ((size_t)b * C + c0) * S;
     const int n = cc * S;
     if ((n & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-        const float4 *s4 = reinterpret_cast<const float4 *>(src);
-        float4 *d4 = reinterpret_cast<float4 *>(rows);
-        for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
+        stage_rows_bulk(rows, src, (unsigned)n * 4u, bar);   // whole rows in flight, no register pass
     } else {
         for (int t = threadIdx.x; t < n; t += blockDim.x) rows[t] = __ldg(src + t);
+        __syncthreads();
     }
-    __syncthreads();
     const int q0 = blockIdx.x * q_per_cta;          // multiple of 4
     const int q1 = min(Q, q0 + q_per_cta);          // Q is a multiple of 4
     float *dst = out + ((size_t)b * C + c0) * Q;
@@ -658,7 +690,7 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
                 static bool optin_done = false;
                 if (!optin_done) {
                     FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    max_smem_optin()));
+                                                    max_smem_optin() - 1024));
                     optin_done = true;
                 }
                 kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, CC, (int)q_per_cta);
@@ -670,7 +702,7 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         static bool optin_done = false;   // once per instantiation (not a stream op: keep it out of graphs)
         if (!optin_done) {
             FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            max_smem_optin()));
+                                            max_smem_optin() - 1024));
             optin_done = true;
         }
         kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, CC,
@@ -697,7 +729,7 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         static bool optin_done = false;
         if (!optin_done) {
             FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            max_smem_optin()));
+                                            max_smem_optin() - 1024));
             optin_done = true;
         }
         dim3 grid((unsigned)ceil_div(Q, q_per_cta), (unsigned)C, (unsigned)B);
