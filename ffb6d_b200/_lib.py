@@ -49,6 +49,7 @@ def _load():
         "ffb6d_knn_grid_build": (ci, [vp, i64, i64, ci, vp, sz, vp]),
         "ffb6d_knn_grid_query": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp, sz, vp]),
         "ffb6d_knn_grid_tune": (None, [fp, ci]),
+        "ffb6d_knn_grid_tune_k1": (None, [fp]),
         "ffb6d_knn_batch_host": (ci, [vp, sz, sz, sz, vp, sz, sz, vp]),
         "ffb6d_knn_host": (ci, [vp, sz, sz, vp, sz, sz, vp]),
         "ffb6d_gather_max_fwd": (ci, [vp, vp, ci, i64, i64, i64, i64, ci, ci, vp, vp]),

@@ -166,6 +166,7 @@ int ffb6d_knn_grid_query(const float *support, const float *query, int64_t B, in
 }
 
 void ffb6d_knn_grid_tune(float cell_scale, int quantile) { knn_grid_tune(cell_scale, quantile); }
+void ffb6d_knn_grid_tune_k1(float cell_scale_k1) { knn_grid_tune_k1(cell_scale_k1); }
 
 int ffb6d_knn_batch_host(const float *batch_data, size_t batch_size, size_t npts, size_t dim,
                          const float *queries, size_t nqueries, size_t K, long *batch_indices)

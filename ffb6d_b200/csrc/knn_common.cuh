@@ -87,6 +87,7 @@ int knn_grid_launch(const float *support, const float *query, int64_t B, int64_t
                     cudaStream_t st);
 // build once, query many times (knn_grid.cu)
 void knn_grid_tune(float cell_scale, int quantile);
+void knn_grid_tune_k1(float cell_scale_k1);
 size_t knn_grid_store_bytes(int64_t B, int64_t S);
 size_t knn_grid_query_bytes(int64_t B, int64_t Q);
 int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid_mem,

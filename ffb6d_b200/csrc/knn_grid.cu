@@ -32,6 +32,7 @@
 #include "knn_common.cuh"
 
 #include <algorithm>
+#include <cooperative_groups.h>
 #include <math.h>
 #include <stdlib.h>
 
@@ -85,7 +86,7 @@ struct QueryScratch {
 
 static size_t max_cells_for(int64_t S)
 {
-    size_t m = (size_t)S * 8;
+    size_t m = (size_t)S * 8;   // 32 cells per point measured slower (more empty rows to look up)
     if (m < 4096) m = 4096;
     if (m > ((size_t)1 << 22)) m = (size_t)1 << 22;
     return (m + TILE_CELLS - 1) / TILE_CELLS * TILE_CELLS;   // whole scan tiles, 16-byte aligned rows
@@ -579,7 +580,9 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
     // not certified: hand over to the full scan, unless this query is bit-identical to the
     // item's first far query (then it only needs a copy of that query's row)
     QueryState *Pw = state_all + b;
-    int rep = atomicCAS(&Pw->rep_q, 0, q + 1) - 1;   // stored as q+1 so that all-zero means 'none'
+    int rep = *(volatile int *)&Pw->rep_q;            // stored as q+1 so that all-zero means 'none'
+    if (rep == 0) rep = atomicCAS(&Pw->rep_q, 0, q + 1);
+    rep -= 1;
     bool dup = false;
     if (rep != -1 && rep != q) {
         const float *rp = query + ((size_t)b * Q + rep) * 3;
@@ -587,11 +590,18 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
         // every support point are bit-identical; NaN never compares equal
         dup = (__ldg(rp) == qx) && (__ldg(rp + 1) == qy) && (__ldg(rp + 2) == qz);
     }
+    // one atomic per group of lanes that got here together (hole pixels are spread over all warps)
     if (dup) {
-        const int slot = atomicAdd(&Pw->dup_count, 1);
+        auto g = cooperative_groups::coalesced_threads();
+        int base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(&Pw->dup_count, (int)g.size());
+        const int slot = g.shfl(base, 0) + (int)g.thread_rank();
         ovf_all[(size_t)b * Q + (Q - 1 - slot)] = q;
     } else {
-        const int slot = atomicAdd(&Pw->ovf_count, 1);
+        auto g = cooperative_groups::coalesced_threads();
+        int base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(&Pw->ovf_count, (int)g.size());
+        const int slot = g.shfl(base, 0) + (int)g.thread_rank();
         ovf_all[(size_t)b * Q + slot] = q;
     }
 }
@@ -957,6 +967,7 @@ grid_dup_copy_kernel(int Q, int K, const QueryState *__restrict__ state_all,
 // ------------------------------------------------------------------ host
 static bool g_force_thread_search = false;   // FFB6D_GRID_THREAD_SEARCH=1: one thread per query for every K
 static float g_cell_scale = 1.0f;
+static float g_cell_scale_k1 = 2.5f;   // grids built for K = 1 searches (measured optimum 2 ... 2.8)
 static int g_quantile = 17;
 static bool g_env_read = false;
 
@@ -964,6 +975,7 @@ static void read_env()
 {
     if (g_env_read) return;   // tuning knobs for experiments; results never depend on them
     if (const char *e = getenv("FFB6D_GRID_SCALE")) g_cell_scale = (float)atof(e);
+    if (const char *e = getenv("FFB6D_GRID_SCALE_K1")) g_cell_scale_k1 = (float)atof(e);
     if (const char *e = getenv("FFB6D_GRID_THREAD_SEARCH")) g_force_thread_search = atoi(e) != 0;
     if (const char *e = getenv("FFB6D_GRID_QUANTILE")) g_quantile = std::min(31, std::max(0, atoi(e)));
     g_env_read = true;
@@ -974,6 +986,12 @@ void knn_grid_tune(float cell_scale, int quantile)
     read_env();
     if (cell_scale > 0.f) g_cell_scale = cell_scale;
     if (quantile >= 0) g_quantile = std::min(31, quantile);
+}
+
+void knn_grid_tune_k1(float cell_scale_k1)
+{
+    read_env();
+    if (cell_scale_k1 > 0.f) g_cell_scale_k1 = cell_scale_k1;
 }
 
 template <int KCAP, typename IdxT>
@@ -1049,7 +1067,7 @@ int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid
     if (ceil_div(S, chunk) > MAX_CHUNKS) chunk = (int)ceil_div(S, MAX_CHUNKS);
     const int nchunks = (int)ceil_div(S, chunk);
     grid_prepare_kernel<<<dim3((unsigned)nchunks, (unsigned)B), PREP_THREADS, 0, st>>>(
-        support, (int)S, K, chunk, nchunks, (int)w.maxc, (int)w.ntiles, g_cell_scale, g_quantile,
+        support, (int)S, K, chunk, nchunks, (int)w.maxc, (int)w.ntiles, K == 1 ? g_cell_scale_k1 : g_cell_scale, g_quantile,
         w.params, w.ticket, w.partial);
     FFB6D_LAUNCH_OK("grid_prepare_kernel");
     dim3 tgrid((unsigned)w.ntiles, (unsigned)B);

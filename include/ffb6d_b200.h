@@ -116,6 +116,8 @@ int ffb6d_knn_grid_query(const float *support, const float *query,
  * cell_scale x the `quantile`-th smallest (0..31) of 32 sampled K-th-neighbour distances.
  * Non-positive / negative arguments leave a knob unchanged.  Defaults 1.0 and 17. */
 void ffb6d_knn_grid_tune(float cell_scale, int quantile);
+/* Same knob for the grids built for K = 1 searches (default 2.5). */
+void ffb6d_knn_grid_tune_k1(float cell_scale_k1);
 
 /* HOST-pointer twins with the reference's exact signatures (NN/knn_.h:2-16);
  * dim must be 3.  `long` is int64 on LP64, as in the reference. */
