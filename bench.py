@@ -495,7 +495,8 @@ def main():
                                  "note": "kind::tf32 peak taken as half the measured bf16 peak; 3xTF32 split for "
                                          "fp32 fidelity (1e-5 contract)"},
                     "note": "28 fused cat+conv1x1+BN(eval)+ReLU layers of the fusion stack (models/ffb6d.py:55-80,"
-                            "104-129), frames_per_gpu x 34.1 GFLOP; not part of `value`"}
+                            "104-129), frames_per_gpu x 34.1 GFLOP; not part of `value`; weights split into TF32 hi/lo "
+                            "tiles once at load (ffb6d_fusion_mlp_pack), activations split in the kernel"}
         del mlps
         torch.cuda.empty_cache()
 

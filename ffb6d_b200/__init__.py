@@ -17,7 +17,8 @@ include/ffb6d_b200.h); there is no CPU fallback.
 """
 from . import _lib  # noqa: F401  (raises if the CUDA library is not built)
 from .ops import (knn_search, random_sample, nearest_interpolation, gather_neighbour,  # noqa: F401
-                  relative_pos_encoding, choose_gather, grid_sub_sampling, KnnGrid, backproject, fusion_mlp, fold_batchnorm, att_pool)
+                  relative_pos_encoding, choose_gather, grid_sub_sampling, KnnGrid, backproject, fusion_mlp, fusion_mlp_pack, PackedWeight, fold_batchnorm,
+                  att_pool)
 from . import randla  # noqa: F401
 from .schedule import (build_ffb6d_indices, build_ffb6d_indices_from_depth, knn_schedule,  # noqa: F401
                        gather_schedule)
@@ -25,6 +26,6 @@ from .helper_tool import DataProcessing  # noqa: F401
 
 __all__ = [
     "knn_search", "random_sample", "nearest_interpolation", "gather_neighbour",
-    "relative_pos_encoding", "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fold_batchnorm", "att_pool", "randla", "build_ffb6d_indices", "build_ffb6d_indices_from_depth",
+    "relative_pos_encoding", "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack", "PackedWeight", "fold_batchnorm", "att_pool", "randla", "build_ffb6d_indices", "build_ffb6d_indices_from_depth",
     "knn_schedule", "gather_schedule", "DataProcessing",
 ]

@@ -27,6 +27,8 @@
 //     point axis (NCHW output, no transposition needed because M = output channel = TMEM lane).
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace ffb6d {
 
 constexpr int TM = 128, TN = 128, TK = 32;            // CTA tile
@@ -292,28 +294,373 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
     if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(2 * TN));
 }
 
+
+// ===================================================================== packed-weight kernel
+// The weights are constants at inference: their hi/lo split is computed once
+// (fusion_mlp_pack_kernel) and written in exactly the shared-memory image the A operand needs, one
+// contiguous 32 KB block per (128-row tile, 32-column k-tile): [A_hi | A_lo], each 8 chunks x 128
+// rows x 16 B.  The main kernel is warp-specialised:
+//   warps 0-7  stage the activations (global -> registers -> split -> UMMA layout), drain the
+//              accumulator chunks into round-to-nearest register sums, run the epilogue
+//   warp  8    producer: one cp.async.bulk (TMA, no tensor map needed for a flat block) per k-tile
+//              brings the packed A block straight into shared memory
+//   warp  9    issues the tcgen05.mma's as soon as both halves of a stage have landed
+// Three stages, mbarriers only (no CTA-wide barrier in the main loop): full_a (TMA transaction
+// bytes), full_b (one arrival per staging warp), empty (tcgen05.commit), chunk (as above).
+// Layers with K <= 128 (one accumulation chunk; the P = 76800 / 19200 image-map layers, which are
+// bound by their activation traffic, not by the MMAs) use the DIRECT variant: a single stage and no
+// register sums, so that two CTAs fit on an SM and one's prologue / epilogue overlaps the other's
+// main loop.
+constexpr int PACK_BLOCK_BYTES = 2 * TILE_BYTES;                 // A_hi + A_lo of one k-tile
+constexpr int MLP2_THREADS = 320;
+constexpr int mlp2_smem(int nst) { return nst * STAGE_BYTES + 128; }
+
+__global__ void __launch_bounds__(256)
+fusion_mlp_pack_kernel(const float *__restrict__ w, int Co, int Ci, int nk, int nblocks, float4 *__restrict__ packed)
+{
+    const long long o = (long long)blockIdx.x * blockDim.x + threadIdx.x;   // one (block, chunk, row) each
+    if (o >= (long long)nblocks * 1024) return;
+    const int blk = (int)(o >> 10), r = (int)(o & 1023), c = r >> 7, m = r & 127;
+    const int gm = (blk / nk) * TM + m, gk = (blk % nk) * TK + 4 * c;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (gm < Co) {
+        const float *src = w + (size_t)gm * Ci + gk;
+        if (gk + 0 < Ci) v.x = __ldg(src + 0);
+        if (gk + 1 < Ci) v.y = __ldg(src + 1);
+        if (gk + 2 < Ci) v.z = __ldg(src + 2);
+        if (gk + 3 < Ci) v.w = __ldg(src + 3);
+    }
+    float4 hi, lo;
+    split4(v, hi, lo);
+    float4 *dst = packed + (size_t)blk * (PACK_BLOCK_BYTES / 16);
+    dst[r] = hi;
+    dst[TILE_BYTES / 16 + r] = lo;
+}
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
+}
+
+template <int NST, bool DIRECT>
+__global__ void __launch_bounds__(MLP2_THREADS, DIRECT ? 3 : 1)
+fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
+                         const unsigned char *__restrict__ wpack, const float *__restrict__ scale,
+                         const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
+                         float slope)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * STAGE_BYTES);
+    uint64_t *full_a = bars, *full_b = bars + NST, *empty = bars + 2 * NST, *chunk = bars + 3 * NST;   // 11 barriers
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NST * STAGE_BYTES + 96);
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int b = blockIdx.z, m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int Ci = C1 + C2;
+    const int nk = (Ci + TK - 1) / TK;
+
+    if (wid == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(DIRECT ? TN : 2 * TN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    }
+    if (tid == 32) {
+        for (int i = 0; i < NST; ++i) {
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(full_a + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" :: "r"(smem_u32(full_b + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(empty + i)));
+        }
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(chunk + 0)));
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(chunk + 1)));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_d = *tmem_slot;
+
+    if (wid == 8) {
+        // ---------------- A producer
+        if (lane == 0) {
+            const unsigned char *src = wpack + (size_t)blockIdx.y * nk * PACK_BLOCK_BYTES;
+            for (int kt = 0; kt < nk; ++kt) {
+                const int st = kt % NST, n = kt / NST;
+                if (n >= 1) mbar_wait(smem_u32(empty + st), (uint32_t)((n - 1) & 1));
+                const uint32_t bar = smem_u32(full_a + st);
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(PACK_BLOCK_BYTES) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             :: "r"(smem_u32(smem + st * STAGE_BYTES)), "l"(src + (size_t)kt * PACK_BLOCK_BYTES),
+                                "r"(PACK_BLOCK_BYTES), "r"(bar) : "memory");
+            }
+        }
+        __syncwarp();
+    } else if (wid == 9) {
+        // ---------------- MMA issuer
+        if (lane == 0) {
+            for (int kt = 0; kt < nk; ++kt) {
+                const int st = kt % NST, n = kt / NST;
+                mbar_wait(smem_u32(full_a + st), (uint32_t)(n & 1));
+                mbar_wait(smem_u32(full_b + st), (uint32_t)(n & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES), a_lo = a_hi + TILE_BYTES;
+                const uint32_t b_hi = a_lo + TILE_BYTES, b_lo = b_hi + TILE_BYTES;
+                const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
+#pragma unroll
+                for (int j = 0; j < TK / 8; ++j) {
+                    const uint32_t off = j * 2 * CHUNK_BYTES;
+                    umma_tf32(d_buf, umma_desc(a_hi + off), umma_desc(b_hi + off), (kt % CH != 0 || j > 0) ? 1u : 0u);
+                    umma_tf32(d_buf, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
+                    umma_tf32(d_buf, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
+                }
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             :: "r"(smem_u32(empty + st)) : "memory");
+                if (kt % CH == CH - 1 || kt == nk - 1)
+                    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                                 :: "r"(smem_u32(chunk + ((kt / CH) & 1))) : "memory");
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---------------- activation staging, accumulator drain, epilogue
+        const float *xb1 = x1 + (size_t)b * C1 * P;
+        const float *xb2 = x2 ? x2 + (size_t)b * C2 * P : nullptr;
+        const bool vec = ((P & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb1) & 15) == 0) &&
+                         (!xb2 || (reinterpret_cast<uintptr_t>(xb2) & 15) == 0) &&
+                         ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+        const int q = wid & 3, half = wid >> 2;
+        float acc[DIRECT ? 1 : 64];
+#pragma unroll
+        for (int i = 0; i < (DIRECT ? 1 : 64); ++i) acc[i] = 0.f;
+        // columns 64*half + 32*i .. +31 of accumulator `buf`, this thread's row
+        auto tmem_load32 = [&](int buf, int i, uint32_t (&v)[32]) {
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + 64 * half + 32 * i);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        };
+        auto drain = [&](int c) {
+            if constexpr (!DIRECT) {
+                const int buf = c & 1;
+                mbar_wait(smem_u32(chunk + buf), (uint32_t)((c >> 1) & 1));
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {
+                    uint32_t v[32];
+                    tmem_load32(buf, i, v);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) acc[32 * i + j] = __fadd_rn(acc[32 * i + j], __uint_as_float(v[j]));
+                }
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            }
+        };
+        const int kg = wid, ng = lane;   // this thread's 4(k) x 4(n) block of the X tile
+        auto load_b = [&](int kt, float4 (&rb)[4]) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int gk = kt * TK + 4 * kg + j, gn = n0 + 4 * ng;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (gk < Ci) {
+                    const float *row = (gk < C1) ? xb1 + (size_t)gk * P : xb2 + (size_t)(gk - C1) * P;
+                    if (vec && gn + 3 < P) {
+                        v = __ldg(reinterpret_cast<const float4 *>(row + gn));
+                    } else {
+                        if (gn + 0 < P) v.x = __ldg(row + gn + 0);
+                        if (gn + 1 < P) v.y = __ldg(row + gn + 1);
+                        if (gn + 2 < P) v.z = __ldg(row + gn + 2);
+                        if (gn + 3 < P) v.w = __ldg(row + gn + 3);
+                    }
+                }
+                rb[j] = v;
+            }
+        };
+        auto store_b = [&](int st, const float4 (&rb)[4]) {
+            unsigned char *sB_hi = smem + st * STAGE_BYTES + 2 * TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
+            const float4 t0 = make_float4(rb[0].x, rb[1].x, rb[2].x, rb[3].x);   // n = 4ng + 0, k = 4kg .. 4kg+3
+            const float4 t1 = make_float4(rb[0].y, rb[1].y, rb[2].y, rb[3].y);
+            const float4 t2 = make_float4(rb[0].z, rb[1].z, rb[2].z, rb[3].z);
+            const float4 t3 = make_float4(rb[0].w, rb[1].w, rb[2].w, rb[3].w);
+            unsigned char *bh = sB_hi + kg * CHUNK_BYTES + (4 * ng) * 16, *bl = sB_lo + kg * CHUNK_BYTES + (4 * ng) * 16;
+            float4 hi, lo;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {   // rotated slots: every quarter-warp covers all 32 banks
+                const int x = (i + (ng >> 1)) & 3;
+                const float4 tx = (x == 0) ? t0 : (x == 1) ? t1 : (x == 2) ? t2 : t3;
+                split4(tx, hi, lo);
+                *reinterpret_cast<float4 *>(bh + 16 * x) = hi;
+                *reinterpret_cast<float4 *>(bl + 16 * x) = lo;
+            }
+        };
+        float4 rb[4], nb[4];
+        load_b(0, rb);
+        for (int kt = 0; kt < nk; ++kt) {
+            const int st = kt % NST, n = kt / NST;
+            if (kt + 1 < nk) load_b(kt + 1, nb);
+            if (n >= 1) mbar_wait(smem_u32(empty + st), (uint32_t)((n - 1) & 1));   // MMAs that read this stage are done
+            store_b(st, rb);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(full_b + st));
+            // the previous chunk is drained while the tensor core works on this one
+            if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) rb[i] = nb[i];
+        }
+        if constexpr (DIRECT) {   // single chunk: the epilogue reads the accumulator itself
+            mbar_wait(smem_u32(chunk), 0u);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        } else {
+            drain((nk - 1) / CH);
+        }
+        const int gm = m0 + 32 * q + lane;
+        const bool row_ok = gm < Co;
+        const float sc = row_ok ? __ldg(scale + gm) : 0.f, sh = row_ok ? __ldg(shift + gm) : 0.f;
+        float *orow = out + ((size_t)b * Co + (row_ok ? gm : 0)) * P;
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            uint32_t v[32];
+            if constexpr (DIRECT) {
+                tmem_load32(0, i, v);   // warp-collective: rows beyond Co take part, they just do not store
+            } else {
+#pragma unroll
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[32 * i + j]);
+            }
+            if (row_ok) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) {
+                    const int gn = n0 + 64 * half + 32 * i + j;
+                    float y[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        y[u] = __fadd_rn(__fmul_rn(__uint_as_float(v[j + u]), sc), sh);
+                        if (act == 1) y[u] = fmaxf(y[u], 0.f);
+                        else if (act == 2) y[u] = (y[u] > 0.f) ? y[u] : __fmul_rn(y[u], slope);
+                    }
+                    if (vec && gn + 3 < P) {
+                        *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
+                    } else {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (gn + u < P) orow[gn + u] = y[u];
+                    }
+                }
+            }
+        }
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(DIRECT ? TN : 2 * TN));
+}
+
 }  // namespace ffb6d
 
 using namespace ffb6d;
 
-extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C2, const float *weight,
-                                    const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
-                                    int act, float negative_slope, float *out, ffb6d_stream_t stream)
+static int mlp_check(const void *x1, int64_t C1, const void *x2, int64_t C2, const void *weight, const void *scale,
+                     const void *shift, int64_t B, int64_t Co, int64_t P, int act, const void *out)
 {
     FFB6D_CHECK_ARG(B >= 0 && C1 >= 1 && C2 >= 0 && Co >= 1 && P >= 0, "fusion_mlp_fwd: bad size");
     FFB6D_CHECK_ARG(act >= 0 && act <= 2, "fusion_mlp_fwd: act=%d (0 none, 1 ReLU, 2 LeakyReLU)", act);
     FFB6D_CHECK_ARG(B < 65536 && Co <= 65535ll * TM && P < (1ll << 31) && C1 + C2 < (1ll << 31),
                     "fusion_mlp_fwd: size too large");
-    if (B == 0 || P == 0) return FFB6D_OK;
+    if (B == 0 || P == 0) return 1;   // nothing to do
     FFB6D_CHECK_ARG(x1 && weight && scale && shift && out && (C2 == 0 || x2), "fusion_mlp_fwd: null pointer");
+    return FFB6D_OK;
+}
+
+extern "C" size_t ffb6d_fusion_mlp_pack_bytes(int64_t Co, int64_t Ci)
+{
+    if (Co < 1 || Ci < 1) return 0;
+    return (size_t)ceil_div(Co, TM) * (size_t)ceil_div(Ci, TK) * PACK_BLOCK_BYTES;
+}
+
+extern "C" int ffb6d_fusion_mlp_pack(const float *weight, int64_t Co, int64_t Ci, void *packed, size_t packed_bytes,
+                                     ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(weight && packed && Co >= 1 && Ci >= 1 && Ci < (1ll << 31) && Co <= 65535ll * TM,
+                    "fusion_mlp_pack: bad argument");
+    const size_t need = ffb6d_fusion_mlp_pack_bytes(Co, Ci);
+    if (packed_bytes < need) {
+        set_error("fusion_mlp_pack: %zu bytes required, %zu given", need, packed_bytes);
+        return FFB6D_ERR_WORKSPACE;
+    }
+    FFB6D_CHECK_ARG((reinterpret_cast<uintptr_t>(packed) & 15) == 0, "fusion_mlp_pack: packed must be 16-byte aligned");
+    const int nk = (int)ceil_div(Ci, TK), nblocks = (int)(ceil_div(Co, TM) * nk);
+    fusion_mlp_pack_kernel<<<(unsigned)ceil_div((int64_t)nblocks * 1024, 256), 256, 0, (cudaStream_t)stream>>>(
+        weight, (int)Co, (int)Ci, nk, nblocks, (float4 *)packed);
+    FFB6D_LAUNCH_OK("fusion_mlp_pack_kernel");
+    return FFB6D_OK;
+}
+
+extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const float *x2, int64_t C2, const void *packed,
+                                           const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
+                                           int act, float negative_slope, float *out, ffb6d_stream_t stream)
+{
+    const int rc = mlp_check(x1, C1, x2, C2, packed, scale, shift, B, Co, P, act, out);
+    if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
     static bool optin_done = false;
     if (!optin_done) {
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM));
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        mlp2_smem(3)));
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        mlp2_smem(1)));
         optin_done = true;
     }
     dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
-    fusion_mlp_kernel<<<grid, 256, MLP_SMEM, (cudaStream_t)stream>>>(x1, (int)C1, C2 ? x2 : nullptr, (int)C2, weight,
-                                                                    scale, shift, out, (int)Co, (int)P, act, negative_slope);
-    FFB6D_LAUNCH_OK("fusion_mlp_kernel");
+    static const bool no_direct = getenv("FFB6D_MLP_NO_DIRECT") != nullptr;
+    if (ceil_div(C1 + C2, TK) <= CH && !no_direct)
+        fusion_mlp_packed_kernel<1, true><<<grid, MLP2_THREADS, mlp2_smem(1), (cudaStream_t)stream>>>(
+            x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
+            act, negative_slope);
+    else
+        fusion_mlp_packed_kernel<3, false><<<grid, MLP2_THREADS, mlp2_smem(3), (cudaStream_t)stream>>>(
+            x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
+            act, negative_slope);
+    FFB6D_LAUNCH_OK("fusion_mlp_packed_kernel");
     return FFB6D_OK;
+}
+
+extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C2, const float *weight,
+                                    const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
+                                    int act, float negative_slope, float *out, ffb6d_stream_t stream)
+{
+    const int rc = mlp_check(x1, C1, x2, C2, weight, scale, shift, B, Co, P, act, out);
+    if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
+    static const bool v1 = getenv("FFB6D_MLP_V1") != nullptr;   // the first-generation kernel (threads stage W too)
+    if (v1) {
+        static bool optin_done = false;
+        if (!optin_done) {
+            FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM));
+            optin_done = true;
+        }
+        dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
+        fusion_mlp_kernel<<<grid, 256, MLP_SMEM, (cudaStream_t)stream>>>(x1, (int)C1, C2 ? x2 : nullptr, (int)C2, weight,
+                                                                        scale, shift, out, (int)Co, (int)P, act,
+                                                                        negative_slope);
+        FFB6D_LAUNCH_OK("fusion_mlp_kernel");
+        return FFB6D_OK;
+    }
+    // raw weights: split them into a stream-ordered scratch block first (callers that keep their
+    // weights should pack once with ffb6d_fusion_mlp_pack and call ffb6d_fusion_mlp_fwd_packed)
+    const size_t bytes = ffb6d_fusion_mlp_pack_bytes(Co, C1 + C2);
+    static bool pool_set = false;
+    if (!pool_set) {   // keep freed scratch blocks in the stream-ordered pool instead of returning them to the OS
+        int dev = 0;
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
+            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+        pool_set = true;
+    }
+    void *scratch = nullptr;
+    FFB6D_CUDA(cudaMallocAsync(&scratch, bytes, (cudaStream_t)stream));
+    int r = ffb6d_fusion_mlp_pack(weight, Co, C1 + C2, scratch, bytes, stream);
+    if (r == FFB6D_OK)
+        r = ffb6d_fusion_mlp_fwd_packed(x1, C1, x2, C2, scratch, scale, shift, B, Co, P, act, negative_slope, out, stream);
+    cudaFreeAsync(scratch, (cudaStream_t)stream);
+    return r;
 }

@@ -344,6 +344,27 @@ def fold_batchnorm(bn):
     return scale.contiguous(), (beta - mean * scale).contiguous()
 
 
+class PackedWeight:
+    """``conv.weight`` of a 1x1 layer split into TF32 hi/lo tiles for :func:`fusion_mlp`
+    (``ffb6d_fusion_mlp_pack``).  Build it once per layer at load time (inference)."""
+
+    def __init__(self, weight):
+        _need_cuda(weight, "weight")
+        w = weight.detach().reshape(weight.shape[0], -1).contiguous().float()
+        self.Co, self.Ci = int(w.shape[0]), int(w.shape[1])
+        self.device = w.device
+        nbytes = lib.ffb6d_fusion_mlp_pack_bytes(self.Co, self.Ci)
+        self.data = torch.empty(nbytes, dtype=torch.uint8, device=w.device)
+        with torch.cuda.device(w.device):
+            check(lib.ffb6d_fusion_mlp_pack(w.data_ptr(), self.Co, self.Ci, self.data.data_ptr(), nbytes,
+                                            _stream(w.device)))
+
+
+def fusion_mlp_pack(weight):
+    """Prepare a layer's weights for repeated :func:`fusion_mlp` calls (returns a :class:`PackedWeight`)."""
+    return PackedWeight(weight)
+
+
 def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
     """``relu(scale * conv1x1(cat(x1, x2, dim=1)) + shift)`` in one tensor-core kernel
     (``ffb6d_fusion_mlp_fwd``): the fusion layers of FFB6D (models/ffb6d.py:55-80, 104-129 applied
@@ -352,7 +373,8 @@ def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
 
     :param x1: ``[B, C1, N, 1]`` / ``[B, C1, H, W]`` / ``[B, C1, N]`` float32 CUDA, NCHW-contiguous
     :param x2: second input of the concat with the same trailing shape, or ``None``
-    :param weight: ``[Co, C1+C2]`` or ``[Co, C1+C2, 1, 1]`` (``conv.weight``)
+    :param weight: ``[Co, C1+C2]`` or ``[Co, C1+C2, 1, 1]`` (``conv.weight``), or the
+      :class:`PackedWeight` made from it by :func:`fusion_mlp_pack` (skips the per-call split)
     :param scale, shift: ``[Co]`` folded BatchNorm (:func:`fold_batchnorm`); pass ones / the conv
       bias for a layer without BatchNorm
     :param relu: apply ReLU; with ``negative_slope`` given, LeakyReLU(negative_slope) instead (RandLA's
@@ -374,19 +396,27 @@ def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
             raise ValueError("x2 must be float32 with the batch and trailing shape of x1")
         x2c = x2.contiguous()
         C2 = x2.shape[1]
-    w = weight.reshape(weight.shape[0], -1).contiguous().float()
-    Co = w.shape[0]
-    if w.shape[1] != C1 + C2:
-        raise ValueError("weight has %d input channels, inputs have %d" % (w.shape[1], C1 + C2))
+    packed = weight if isinstance(weight, PackedWeight) else None
+    if packed is not None:
+        Co, Ci = packed.Co, packed.Ci
+        if packed.device != x1.device:
+            raise ValueError("packed weight lives on %s, inputs on %s" % (packed.device, x1.device))
+    else:
+        w = weight.reshape(weight.shape[0], -1).contiguous().float()
+        Co, Ci = w.shape[0], w.shape[1]
+    if Ci != C1 + C2:
+        raise ValueError("weight has %d input channels, inputs have %d" % (Ci, C1 + C2))
     sc, sh = scale.contiguous().float(), shift.contiguous().float()
     if sc.numel() != Co or sh.numel() != Co:
         raise ValueError("scale/shift must have %d elements" % Co)
     out = torch.empty((B, Co) + tail, dtype=torch.float32, device=x1.device)
+    fn = lib.ffb6d_fusion_mlp_fwd_packed if packed is not None else lib.ffb6d_fusion_mlp_fwd
+    wptr = packed.data.data_ptr() if packed is not None else w.data_ptr()
     with torch.cuda.device(x1.device):
-        check(lib.ffb6d_fusion_mlp_fwd(x1c.data_ptr(), C1, x2c.data_ptr() if x2c is not None else None, C2,
-                                       w.data_ptr(), sc.data_ptr(), sh.data_ptr(), B, Co, P,
-                                       2 if negative_slope is not None else int(bool(relu)),
-                                       float(negative_slope or 0.0), out.data_ptr(), _stream(x1.device)))
+        check(fn(x1c.data_ptr(), C1, x2c.data_ptr() if x2c is not None else None, C2,
+                 wptr, sc.data_ptr(), sh.data_ptr(), B, Co, P,
+                 2 if negative_slope is not None else int(bool(relu)),
+                 float(negative_slope or 0.0), out.data_ptr(), _stream(x1.device)))
     return out
 
 

@@ -159,9 +159,10 @@ class FusionMLPs:
     folded into scale/shift), run through the tensor-core kernel.  BASELINE.md reports them
     separately from the KNN + gather pass."""
 
-    def __init__(self, batch, n_points=12288, h=480, w=640, device="cuda", seed=0):
+    def __init__(self, batch, n_points=12288, h=480, w=640, device="cuda", seed=0, prepack=True):
         self.B = batch
         self.device = torch.device(device)
+        self.prepack = prepack   # weights split once at load (inference), as a deployed model would
         self.layers = S.fusion_mlp_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.args = []
@@ -174,7 +175,7 @@ class FusionMLPs:
             wgt = rnd(Co, C1 + C2) / float(C1 + C2) ** 0.5
             scale = torch.rand(Co, generator=g, device=self.device) + 0.5
             shift = rnd(Co) * 0.1
-            self.args.append((x1, x2, wgt, scale, shift))
+            self.args.append((x1, x2, ops.fusion_mlp_pack(wgt) if prepack else wgt, scale, shift))
             self.flops += 2 * batch * Co * (C1 + C2) * P
 
     def __call__(self):

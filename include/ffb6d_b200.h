@@ -200,6 +200,21 @@ int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C
                          float *out, ffb6d_stream_t stream);
 
 /*
+ * The same layer with the weights prepared once (inference: weights are constants).
+ * ffb6d_fusion_mlp_pack splits weight [Co,Ci] into its TF32 hi/lo parts and lays them out as the
+ * kernel's shared-memory tiles (`packed`: device, 16-byte aligned, ffb6d_fusion_mlp_pack_bytes(Co,
+ * Ci) bytes); ffb6d_fusion_mlp_fwd_packed then streams those tiles with bulk-async (TMA) copies.
+ * ffb6d_fusion_mlp_fwd = pack into a stream-ordered scratch block + fwd_packed.
+ */
+size_t ffb6d_fusion_mlp_pack_bytes(int64_t Co, int64_t Ci);
+int ffb6d_fusion_mlp_pack(const float *weight, int64_t Co, int64_t Ci, void *packed, size_t packed_bytes,
+                          ffb6d_stream_t stream);
+int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const float *x2, int64_t C2,
+                                const void *packed, const float *scale, const float *shift,
+                                int64_t B, int64_t Co, int64_t P, int act, float negative_slope,
+                                float *out, ffb6d_stream_t stream);
+
+/*
  * Attentive pooling core of RandLA's Att_pooling (models/RandLA/RandLANet.py:243-248):
  *   out[b,c,n] = sum_k f[b,c,n,k] * softmax_k(att[b,c,n,:])[k],   f = cat(f1, f2) along channels
  *   f1 [B,C1,N,K], f2 [B,C2,N,K] or NULL, att [B,C1+C2,N,K] -> out [B,C1+C2,N]   (f32, K <= 64)

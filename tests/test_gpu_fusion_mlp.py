@@ -72,3 +72,23 @@ def test_fusion_mlp_matches_reference_layer(cuda, case):
     got_lin = F.fusion_mlp(x1, x2, conv.weight, scale, shift, relu=False)
     want_lin = reference_layer(x1, x2, conv, bn, relu=False)
     assert (got_lin.double() - want_lin).abs().max().item() <= 1e-5 * max(want_lin.abs().max().item(), 1.0)
+
+
+@pytest.mark.parametrize("case", [CASES[0], CASES[3], CASES[5]], ids=["ds0", "ds3", "ragged"])
+def test_fusion_mlp_packed_weights_bit_identical(cuda, case):
+    """Weights split once (ffb6d_fusion_mlp_pack) give the same bits as the per-call split, and the
+    pack survives many calls."""
+    B, C1, C2, Co, tail = case
+    g = torch.Generator().manual_seed(7)
+    x1 = torch.randn((B, C1) + tail, generator=g).cuda()
+    x2 = torch.randn((B, C2) + tail, generator=g).cuda() if C2 else None
+    conv, bn = make_layer(C1 + C2, Co, seed=3)
+    scale, shift = F.fold_batchnorm(bn)
+    packed = F.fusion_mlp_pack(conv.weight)
+    assert packed.Co == Co and packed.Ci == C1 + C2
+    want = F.fusion_mlp(x1, x2, conv.weight, scale, shift)
+    for _ in range(3):
+        got = F.fusion_mlp(x1, x2, packed, scale, shift)
+        assert torch.equal(got, want)
+    with pytest.raises(ValueError):
+        F.fusion_mlp(x1[:, :-1], x2, packed, scale, shift)
