@@ -28,6 +28,7 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <type_traits>
 
 namespace ffb6d {
 
@@ -312,7 +313,7 @@ fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict_
 // register sums, so that two CTAs fit on an SM and one's prologue / epilogue overlaps the other's
 // main loop.
 constexpr int PACK_BLOCK_BYTES = 2 * TILE_BYTES;                 // A_hi + A_lo of one k-tile
-constexpr int MLP2_THREADS = 320;
+constexpr int mlp2_threads(int nsw) { return (nsw + 2) * 32; }   // staging warps + producer + issuer
 constexpr int mlp2_smem(int nst) { return nst * STAGE_BYTES + 128; }
 
 __global__ void __launch_bounds__(256)
@@ -342,8 +343,8 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-template <int NST, bool DIRECT>
-__global__ void __launch_bounds__(MLP2_THREADS, DIRECT ? 3 : 1)
+template <int NST, bool DIRECT, int NSW>
+__global__ void __launch_bounds__(mlp2_threads(NSW), DIRECT ? 3 : 1)
 fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
                          const unsigned char *__restrict__ wpack, const float *__restrict__ scale,
                          const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
@@ -365,7 +366,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
     if (tid == 32) {
         for (int i = 0; i < NST; ++i) {
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(full_a + i)));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 8;" :: "r"(smem_u32(full_b + i)));
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(full_b + i)), "r"(NSW));
             asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(empty + i)));
         }
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(chunk + 0)));
@@ -377,7 +378,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (wid == 8) {
+    if (wid == NSW) {
         // ---------------- A producer
         if (lane == 0) {
             const unsigned char *src = wpack + (size_t)blockIdx.y * nk * PACK_BLOCK_BYTES;
@@ -392,7 +393,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
             }
         }
         __syncwarp();
-    } else if (wid == 9) {
+    } else if (wid == NSW + 1) {
         // ---------------- MMA issuer
         if (lane == 0) {
             for (int kt = 0; kt < nk; ++kt) {
@@ -425,13 +426,14 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
         const bool vec = ((P & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb1) & 15) == 0) &&
                          (!xb2 || (reinterpret_cast<uintptr_t>(xb2) & 15) == 0) &&
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        const int q = wid & 3, half = wid >> 2;
-        float acc[DIRECT ? 1 : 64];
+        constexpr int COLS = 4 * TN / NSW, NI = COLS / 32;   // accumulator columns per thread: 64 or 32
+        const int q = wid & 3, cs = wid >> 2;                 // TMEM lane quarter (fixed by the warp id), column slice
+        float acc[DIRECT ? 1 : COLS];
 #pragma unroll
-        for (int i = 0; i < (DIRECT ? 1 : 64); ++i) acc[i] = 0.f;
-        // columns 64*half + 32*i .. +31 of accumulator `buf`, this thread's row
+        for (int i = 0; i < (DIRECT ? 1 : COLS); ++i) acc[i] = 0.f;
+        // columns COLS*cs + 32*i .. +31 of accumulator `buf`, this thread's row
         auto tmem_load32 = [&](int buf, int i, uint32_t (&v)[32]) {
-            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + 64 * half + 32 * i);
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + COLS * cs + 32 * i);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
                 "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
@@ -449,7 +451,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 mbar_wait(smem_u32(chunk + buf), (uint32_t)((c >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < 2; ++i) {
+                for (int i = 0; i < NI; ++i) {
                     uint32_t v[32];
                     tmem_load32(buf, i, v);
 #pragma unroll
@@ -458,44 +460,67 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
         };
-        const int kg = wid, ng = lane;   // this thread's 4(k) x 4(n) block of the X tile
-        auto load_b = [&](int kt, float4 (&rb)[4]) {
+        // X tile (32 k x 128 n): warp -> K chunk kg (4 k rows); with 8 staging warps a lane takes 4 n
+        // (128-bit loads), with 16 the two warps of a chunk take 64 n each and a lane 2 n (64-bit loads).
+        // Either way a thread ends up with whole 16-byte (n; k..k+3) slots of the K-major UMMA layout.
+        constexpr int NPL = (NSW == 8) ? 4 : 2;                 // n per lane
+        typedef typename std::conditional<NSW == 8, float4, float2>::type ldt;
+        const int kg = wid & 7, nl = (NSW == 8) ? 4 * lane : 64 * (wid >> 3) + 2 * lane;
+        auto load_b = [&](int kt, ldt (&rb)[4]) {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int gk = kt * TK + 4 * kg + j, gn = n0 + 4 * ng;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int gk = kt * TK + 4 * kg + j, gn = n0 + nl;
+                float e[4] = {0.f, 0.f, 0.f, 0.f};
                 if (gk < Ci) {
                     const float *row = (gk < C1) ? xb1 + (size_t)gk * P : xb2 + (size_t)(gk - C1) * P;
-                    if (vec && gn + 3 < P) {
-                        v = __ldg(reinterpret_cast<const float4 *>(row + gn));
+                    if (vec && gn + NPL - 1 < P) {
+                        const ldt v = __ldg(reinterpret_cast<const ldt *>(row + gn));
+                        e[0] = v.x;
+                        e[1] = v.y;
+                        if constexpr (NSW == 8) {
+                            e[2] = v.z;
+                            e[3] = v.w;
+                        }
                     } else {
-                        if (gn + 0 < P) v.x = __ldg(row + gn + 0);
-                        if (gn + 1 < P) v.y = __ldg(row + gn + 1);
-                        if (gn + 2 < P) v.z = __ldg(row + gn + 2);
-                        if (gn + 3 < P) v.w = __ldg(row + gn + 3);
+#pragma unroll
+                        for (int u = 0; u < NPL; ++u)
+                            if (gn + u < P) e[u] = __ldg(row + gn + u);
                     }
                 }
-                rb[j] = v;
+                if constexpr (NSW == 8) rb[j] = make_float4(e[0], e[1], e[2], e[3]);
+                else rb[j] = make_float2(e[0], e[1]);
             }
         };
-        auto store_b = [&](int st, const float4 (&rb)[4]) {
+        auto store_b = [&](int st, const ldt (&rb)[4]) {
             unsigned char *sB_hi = smem + st * STAGE_BYTES + 2 * TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
-            const float4 t0 = make_float4(rb[0].x, rb[1].x, rb[2].x, rb[3].x);   // n = 4ng + 0, k = 4kg .. 4kg+3
-            const float4 t1 = make_float4(rb[0].y, rb[1].y, rb[2].y, rb[3].y);
-            const float4 t2 = make_float4(rb[0].z, rb[1].z, rb[2].z, rb[3].z);
-            const float4 t3 = make_float4(rb[0].w, rb[1].w, rb[2].w, rb[3].w);
-            unsigned char *bh = sB_hi + kg * CHUNK_BYTES + (4 * ng) * 16, *bl = sB_lo + kg * CHUNK_BYTES + (4 * ng) * 16;
+            unsigned char *bh = sB_hi + kg * CHUNK_BYTES + nl * 16, *bl = sB_lo + kg * CHUNK_BYTES + nl * 16;
             float4 hi, lo;
+            if constexpr (NSW == 8) {
+                const float4 t0 = make_float4(rb[0].x, rb[1].x, rb[2].x, rb[3].x);   // n = nl + 0, k = 4kg .. 4kg+3
+                const float4 t1 = make_float4(rb[0].y, rb[1].y, rb[2].y, rb[3].y);
+                const float4 t2 = make_float4(rb[0].z, rb[1].z, rb[2].z, rb[3].z);
+                const float4 t3 = make_float4(rb[0].w, rb[1].w, rb[2].w, rb[3].w);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {   // rotated slots: every quarter-warp covers all 32 banks
-                const int x = (i + (ng >> 1)) & 3;
-                const float4 tx = (x == 0) ? t0 : (x == 1) ? t1 : (x == 2) ? t2 : t3;
-                split4(tx, hi, lo);
-                *reinterpret_cast<float4 *>(bh + 16 * x) = hi;
-                *reinterpret_cast<float4 *>(bl + 16 * x) = lo;
+                for (int i = 0; i < 4; ++i) {   // rotated slots: every quarter-warp covers all 32 banks
+                    const int x = (i + (lane >> 1)) & 3;
+                    const float4 tx = (x == 0) ? t0 : (x == 1) ? t1 : (x == 2) ? t2 : t3;
+                    split4(tx, hi, lo);
+                    *reinterpret_cast<float4 *>(bh + 16 * x) = hi;
+                    *reinterpret_cast<float4 *>(bl + 16 * x) = lo;
+                }
+            } else {
+                const float4 t0 = make_float4(rb[0].x, rb[1].x, rb[2].x, rb[3].x);
+                const float4 t1 = make_float4(rb[0].y, rb[1].y, rb[2].y, rb[3].y);
+#pragma unroll
+                for (int i = 0; i < 2; ++i) {   // 32-byte lane stride: lanes l and l+4 swap slots
+                    const int x = (i + (lane >> 2)) & 1;
+                    split4(x == 0 ? t0 : t1, hi, lo);
+                    *reinterpret_cast<float4 *>(bh + 16 * x) = hi;
+                    *reinterpret_cast<float4 *>(bl + 16 * x) = lo;
+                }
             }
         };
-        float4 rb[4], nb[4];
+        ldt rb[4], nb[4];
         load_b(0, rb);
         for (int kt = 0; kt < nk; ++kt) {
             const int st = kt % NST, n = kt / NST;
@@ -521,7 +546,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
         const float sc = row_ok ? __ldg(scale + gm) : 0.f, sh = row_ok ? __ldg(shift + gm) : 0.f;
         float *orow = out + ((size_t)b * Co + (row_ok ? gm : 0)) * P;
 #pragma unroll
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < NI; ++i) {
             uint32_t v[32];
             if constexpr (DIRECT) {
                 tmem_load32(0, i, v);   // warp-collective: rows beyond Co take part, they just do not store
@@ -532,7 +557,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
             if (row_ok) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4) {
-                    const int gn = n0 + 64 * half + 32 * i + j;
+                    const int gn = n0 + COLS * cs + 32 * i + j;
                     float y[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -604,20 +629,27 @@ extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const fl
     if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
     static bool optin_done = false;
     if (!optin_done) {
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        mlp2_smem(3)));
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<1, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        mlp2_smem(1)));
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false, 16>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(3)));
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false, 8>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(3)));
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<1, true, 8>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(1)));
         optin_done = true;
     }
     dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
     static const bool no_direct = getenv("FFB6D_MLP_NO_DIRECT") != nullptr;
+    static const bool sw8 = getenv("FFB6D_MLP_SW8") != nullptr;   // experiment: 8 staging warps for every layer
     if (ceil_div(C1 + C2, TK) <= CH && !no_direct)
-        fusion_mlp_packed_kernel<1, true><<<grid, MLP2_THREADS, mlp2_smem(1), (cudaStream_t)stream>>>(
+        fusion_mlp_packed_kernel<1, true, 8><<<grid, mlp2_threads(8), mlp2_smem(1), (cudaStream_t)stream>>>(
+            x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
+            act, negative_slope);
+    else if (sw8)
+        fusion_mlp_packed_kernel<3, false, 8><<<grid, mlp2_threads(8), mlp2_smem(3), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
             act, negative_slope);
     else
-        fusion_mlp_packed_kernel<3, false><<<grid, MLP2_THREADS, mlp2_smem(3), (cudaStream_t)stream>>>(
+        fusion_mlp_packed_kernel<3, false, 16><<<grid, mlp2_threads(16), mlp2_smem(3), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
             act, negative_slope);
     FFB6D_LAUNCH_OK("fusion_mlp_packed_kernel");
