@@ -466,7 +466,17 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
         constexpr int NPL = (NSW == 8) ? 4 : 2;                 // n per lane
         typedef typename std::conditional<NSW == 8, float4, float2>::type ldt;
         const int kg = wid & 7, nl = (NSW == 8) ? 4 * lane : 64 * (wid >> 3) + 2 * lane;
+        // fast path: whole tile inside the tensors, vector loads, and a 4-row K chunk never straddles the
+        // concat boundary -> one base pointer per tile, four loads at a row stride
+        const bool fast = vec && ((C1 & 3) == 0) && (n0 + TN <= P);
         auto load_b = [&](int kt, ldt (&rb)[4]) {
+            const int gk0 = kt * TK + 4 * kg;
+            if (fast && gk0 + 3 < Ci) {
+                const float *p0 = ((gk0 < C1) ? xb1 + (size_t)gk0 * P : xb2 + (size_t)(gk0 - C1) * P) + (n0 + nl);
+#pragma unroll
+                for (int j = 0; j < 4; ++j) rb[j] = __ldg(reinterpret_cast<const ldt *>(p0 + (size_t)j * P));
+                return;
+            }
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
                 const int gk = kt * TK + 4 * kg + j, gn = n0 + nl;
