@@ -343,7 +343,7 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-template <int NST, bool DIRECT, int NSW>
+template <int NST, bool DIRECT, int NSW, int PD>
 __global__ void __launch_bounds__(mlp2_threads(NSW), DIRECT ? 3 : 1)
 fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
                          const unsigned char *__restrict__ wpack, const float *__restrict__ scale,
@@ -451,11 +451,18 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 mbar_wait(smem_u32(chunk + buf), (uint32_t)((c >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
-                for (int i = 0; i < NI; ++i) {
-                    uint32_t v[32];
-                    tmem_load32(buf, i, v);
+                for (int i = 0; i < COLS / 16; ++i) {   // 16 columns at a time keeps the temporaries small
+                    uint32_t v[16];
+                    const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + COLS * cs + 16 * i);
+                    asm volatile(
+                        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                          "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                        : "r"(taddr));
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) acc[32 * i + j] = __fadd_rn(acc[32 * i + j], __uint_as_float(v[j]));
+                    for (int j = 0; j < 16; ++j) acc[16 * i + j] = __fadd_rn(acc[16 * i + j], __uint_as_float(v[j]));
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
@@ -530,20 +537,30 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 }
             }
         };
-        ldt rb[4], nb[4];
-        load_b(0, rb);
-        for (int kt = 0; kt < nk; ++kt) {
-            const int st = kt % NST, n = kt / NST;
-            if (kt + 1 < nk) load_b(kt + 1, nb);
-            if (n >= 1) mbar_wait(smem_u32(empty + st), (uint32_t)((n - 1) & 1));   // MMAs that read this stage are done
-            store_b(st, rb);
-            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-            __syncwarp();
-            if (lane == 0) mbar_arrive(smem_u32(full_b + st));
-            // the previous chunk is drained while the tensor core works on this one
-            if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
+        // register ring of PD tiles: tile kt lives in ring[kt % PD]; as soon as it has been written to
+        // shared memory the slot is refilled with tile kt + PD, so PD - 1 .. PD tiles of global-memory
+        // latency are in flight per thread (one tile was not enough: the staging warps sat on the
+        // scoreboard of their own loads)
+        ldt ring[PD][4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) rb[i] = nb[i];
+        for (int d = 0; d < PD; ++d)
+            if (d < nk) load_b(d, ring[d]);
+        for (int kt0 = 0; kt0 < nk; kt0 += PD) {
+#pragma unroll
+            for (int d = 0; d < PD; ++d) {
+                const int kt = kt0 + d;
+                if (kt < nk) {
+                    const int st = kt % NST, n = kt / NST;
+                    if (n >= 1) mbar_wait(smem_u32(empty + st), (uint32_t)((n - 1) & 1));   // MMAs that read this stage are done
+                    store_b(st, ring[d]);
+                    if (kt + PD < nk) load_b(kt + PD, ring[d]);
+                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(smem_u32(full_b + st));
+                    // the previous chunk is drained while the tensor core works on this one
+                    if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
+                }
+            }
         }
         if constexpr (DIRECT) {   // single chunk: the epilogue reads the accumulator itself
             mbar_wait(smem_u32(chunk), 0u);
@@ -639,27 +656,20 @@ extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const fl
     if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
     static bool optin_done = false;
     if (!optin_done) {
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false, 16>,
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false, 16, 3>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(3)));
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false, 8>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(3)));
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<1, true, 8>,
+        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<1, true, 8, 2>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(1)));
         optin_done = true;
     }
     dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
     static const bool no_direct = getenv("FFB6D_MLP_NO_DIRECT") != nullptr;
-    static const bool sw8 = getenv("FFB6D_MLP_SW8") != nullptr;   // experiment: 8 staging warps for every layer
     if (ceil_div(C1 + C2, TK) <= CH && !no_direct)
-        fusion_mlp_packed_kernel<1, true, 8><<<grid, mlp2_threads(8), mlp2_smem(1), (cudaStream_t)stream>>>(
-            x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
-            act, negative_slope);
-    else if (sw8)
-        fusion_mlp_packed_kernel<3, false, 8><<<grid, mlp2_threads(8), mlp2_smem(3), (cudaStream_t)stream>>>(
+        fusion_mlp_packed_kernel<1, true, 8, 2><<<grid, mlp2_threads(8), mlp2_smem(1), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
             act, negative_slope);
     else
-        fusion_mlp_packed_kernel<3, false, 16><<<grid, mlp2_threads(16), mlp2_smem(3), (cudaStream_t)stream>>>(
+        fusion_mlp_packed_kernel<3, false, 16, 3><<<grid, mlp2_threads(16), mlp2_smem(3), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
             act, negative_slope);
     FFB6D_LAUNCH_OK("fusion_mlp_packed_kernel");
