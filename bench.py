@@ -232,8 +232,10 @@ def kernel_family(op_name):
         return parts[2]
     if kind == "knn_build":
         return "grid build (prepare+zero+count+scan+scatter)"
-    k1 = "interp" in key or key.startswith("p2r")
-    return "grid_search_kernel<K=1> (+knn_brute for S<512)" if k1 else "grid_search_warp_kernel<K=16>"  # family label (K = --k)
+    if "interp" in key or key.startswith("p2r"):
+        return "grid_search_kernel<K=1> (+knn_brute for S<512)"
+    # the self searches (cld_nei_idx*) and the r2p searches run different instantiations
+    return "grid_search_warp_kernel<SELF>" if key.startswith("cld_nei") else "grid_search_warp_kernel<non-self>"
 
 
 def main():
@@ -405,7 +407,13 @@ def main():
     i0, i1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     inst_ms, spin_ms, enqueue_ms = 0.0, 0.0, 0.0
-    spin_cycles = int(40e6)   # ~19 ms at 2.1 GHz: the CPU enqueues a whole step (~3 ms) behind it
+    # how long does this box's CPU need to enqueue one instrumented step?  (3 ms ... 25 ms seen on
+    # the pool's hosts.)  The spin has to outlast it, or the event pairs measure launch gaps.
+    c0 = time.perf_counter()
+    p(cld_d, xyz_d, cho_d, OpTimer())
+    dry_ms = (time.perf_counter() - c0) * 1e3
+    torch.cuda.synchronize()
+    spin_cycles = int(min(max(40e6, (1.5 * dry_ms + 5.0) * 2.0e6), 1.2e9))   # cycles at <= 2 GHz
     for _ in range(args.steps):
         s0.record()
         torch.cuda._sleep(spin_cycles)
