@@ -460,6 +460,9 @@ def main():
     roofline = {
         "bound": "hbm", "kernel": dom, "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak, "traffic": traffic, "traffic_capture": cap or None, "peak_source": peak_src,
+        "note": ("the KNN searches are instruction-issue bound (ncu: issue slots 60-75 % busy, DRAM < 2 %): their "
+                 "algorithmic bytes are tiny, so their HBM fraction is informational; the HBM-bound kernels are the "
+                 "gathers (see `families`), the whole pass is `pass_roofline`") if dom.startswith("grid_search") else None,
         "share_of_step": dd["ms"] / tot_ms, "ops_per_step": dd["n"] // steps,
         "alg_bytes_per_launch": dd["bytes"] / dd["n"], "avg_launch_ms": dd["ms"] / dd["n"],
         "families": {k: {"share": v["ms"] / tot_ms, "ms_per_step": v["ms"] / steps,
