@@ -30,6 +30,9 @@ class FusionPass:
         self.layout = layout
         self.index_dtype = index_dtype
         self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1 else None
+        # the gathers (HBM bound) get streams of their own: each waits only for its index tensor, so
+        # it overlaps the searches (issue bound) that are still running
+        self.gstreams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1 else None
         self.gathers = S.gather_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.features = []
@@ -46,9 +49,9 @@ class FusionPass:
         self.gather_alg_bytes_per_frame = gb
 
     # -- the two halves of a pass ------------------------------------------------------
-    def build_indices(self, cld, dpt_xyz, choose, timer=None):
+    def build_indices(self, cld, dpt_xyz, choose, timer=None, events=None):
         inputs = S.build_ffb6d_indices(cld, dpt_xyz, k=self.k, index_dtype=self.index_dtype,
-                                       timer=timer, streams=self.streams)
+                                       timer=timer, streams=self.streams, events=events)
         inputs["choose"] = choose
         return inputs
 
@@ -68,7 +71,9 @@ class FusionPass:
         lay = LAYOUT_NCS if self.layout == "nchw" else LAYOUT_NSC
         return lib.ffb6d_gather_kernel_name(self.B, C, Sz, Q, k, lay).decode()
 
-    def run_gathers(self, inputs, timer=None):
+    def run_gathers(self, inputs, timer=None, events=None):
+        """``events``: per-key events from :func:`build_ffb6d_indices` (side streams not joined yet):
+        every gather waits for its own index tensor only; this call joins all side streams."""
         n = len(self.gathers)
         outs = [None] * n
         if self.streams is None or timer is not None:
@@ -84,13 +89,17 @@ class FusionPass:
         # the 23 gathers are independent of each other too
         main = torch.cuda.current_stream(self.device)
         order = sorted(range(n), key=lambda i: -(self.gathers[i][2] * self.gathers[i][4]))
-        for st in self.streams:
+        gs = self.gstreams if events is not None else self.streams
+        for st in gs:
             st.wait_stream(main)
         for j, i in enumerate(order):
             op, key, C, Sz, Q, K = self.gathers[i]
-            with torch.cuda.stream(self.streams[j % len(self.streams)]):
+            st = gs[j % len(gs)]
+            if events is not None and key in events:
+                st.wait_event(events[key])
+            with torch.cuda.stream(st):
                 outs[i] = self._gather(op, C, self.features[i], inputs[key])
-        for st in self.streams:
+        for st in (self.streams + self.gstreams) if events is not None else gs:
             main.wait_stream(st)
         return outs
 
@@ -143,15 +152,17 @@ class FusionPass:
     def from_depth(self, depth, intr, choose):
         """depth [B,H,W] f32, intr = device (fx,fy,cx,cy) float64 [4]|[B,4], choose [B,1,N] -> pass."""
         cld, pyr = ops.backproject(depth, intr, choose)
+        events = {} if self.streams is not None else None
         inputs = S.build_ffb6d_indices(cld, None, k=self.k, index_dtype=self.index_dtype, streams=self.streams,
-                                       pyramid=pyr, image_hw=(self.h, self.w))
+                                       pyramid=pyr, image_hw=(self.h, self.w), events=events)
         inputs["choose"] = choose
-        return inputs, self.run_gathers(inputs)
+        return inputs, self.run_gathers(inputs, events=events)
 
     def __call__(self, cld, dpt_xyz, choose, timer=None):
         """cld [B,N0,3] f32, dpt_xyz [B,H,W,3] f32, choose [B,1,N0] int -> (inputs dict, outputs)."""
-        inputs = self.build_indices(cld, dpt_xyz, choose, timer)
-        return inputs, self.run_gathers(inputs, timer)
+        events = {} if (self.streams is not None and timer is None) else None
+        inputs = self.build_indices(cld, dpt_xyz, choose, timer, events)
+        return inputs, self.run_gathers(inputs, timer, events)
 
 
 class FusionMLPs:

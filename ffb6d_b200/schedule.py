@@ -134,7 +134,7 @@ def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
 
 
 def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None,
-                        pyramid=None, image_hw=None):
+                        pyramid=None, image_hw=None, events=None):
     """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
 
     :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
@@ -142,6 +142,10 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
       pass ``pyramid={2: [B,HW/4,3], 4: ..., 8: ...}`` + ``image_hw=(H, W)`` (what
       :func:`ffb6d_b200.ops.backproject` returns) and leave it None
     :param streams: optional list of side ``torch.cuda.Stream`` s to overlap the 22 searches on
+    :param events: optional dict; with ``streams`` it receives one ``torch.cuda.Event`` per index
+      key, recorded on the side stream that produced it, and the function returns WITHOUT joining
+      the side streams: the caller waits per key (``stream.wait_event``) and joins ``streams``
+      itself (:class:`ffb6d_b200.pipeline.FusionPass` overlaps the gathers with the remaining searches)
     :param timer: optional object with ``start(name, alg_bytes)`` / ``stop()`` called around
       every KNN call (bench.py's per-op CUDA-event timer)
     :return: dict with the reference's keys (ycb_dataset.py:283-309), each with a leading
@@ -202,6 +206,8 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
         return torch.cuda.stream(streams[i % len(streams)]) if par else contextlib.nullcontext()
 
     fork()
+    # a search waits only for ITS grid, a consumer only for ITS index tensor (events, not joins)
+    built = {}
     for i, g in enumerate(sorted(gridded, key=lambda g: -sets[g[0]].shape[1])):
         with on(i):
             if timer is not None:
@@ -209,8 +215,9 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             grids[g] = KnnGrid(sets[g[0]], g[1])
             if timer is not None:
                 timer.stop()
-    join()
-    fork()
+            if par:
+                built[g] = torch.cuda.Event()
+                built[g].record()
     order = sorted(calls, key=lambda c: -(sets[c[2]].shape[1] * c[3])) if par else calls
     for i, (key, s, q, kk) in enumerate(order):
         sup, qry = sets[s], sets[q]
@@ -218,16 +225,28 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             if timer is not None:
                 timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
             if (s, kk) in grids:
+                if par:
+                    torch.cuda.current_stream(cld.device).wait_event(built[(s, kk)])
                 inputs[key] = grids[(s, kk)].query(qry, kk, out_dtype=index_dtype)
             else:
                 inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype, algo=1)
             if timer is not None:
                 timer.stop()
-    join()
+            done = [key]
+            if key.startswith("cld_nei_idx"):   # cld_sub_idx_i = the first N_{i+1} rows (ycb_dataset.py:279)
+                lvl = int(key[len("cld_nei_idx"):])
+                n_sub = sets[("cld", lvl + 1)].shape[1]
+                inputs["cld_sub_idx%d" % lvl] = inputs[key][:, :n_sub, :].contiguous()
+                done.append("cld_sub_idx%d" % lvl)
+            if par and events is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                for name in done:
+                    events[name] = ev
+    if not (par and events is not None):
+        join()
     for i in range(N_DS_LAYERS):
         inputs["cld_xyz%d" % i] = sets[("cld", i)]
-        n_sub = sets[("cld", i + 1)].shape[1]
-        inputs["cld_sub_idx%d" % i] = inputs["cld_nei_idx%d" % i][:, :n_sub, :].contiguous()
     return inputs
 
 
