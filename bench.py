@@ -251,6 +251,8 @@ def main():
     ap.add_argument("--ref-frames", type=int, default=0, help="frames per CPU-arm sample (0 = #cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-mlp", action="store_true", help="skip the separately reported fusion-MLP timing")
+    ap.add_argument("--streams", type=int, default=2, help="side streams (graph branches) of the index build")
+    ap.add_argument("--gather-streams", type=int, default=0, help="side streams of the gathers (0: same number)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA graph replays")
     ap.add_argument("--per-op", action="store_true", help="also print the per-op table to stderr")
     args = ap.parse_args()
@@ -299,7 +301,8 @@ def main():
     xyz_h = torch.from_numpy(batch["dpt_xyz"]).pin_memory()
     cho_h = torch.from_numpy(batch["choose"]).pin_memory()
     cld_d, xyz_d, cho_d = cld_h.to(dev), xyz_h.to(dev), cho_h.to(dev)
-    p = FusionPass(B, n_points=N0, k=args.k, device=dev, layout=args.layout, seed=rank)
+    p = FusionPass(B, n_points=N0, k=args.k, device=dev, layout=args.layout, seed=rank, n_streams=args.streams,
+                   n_gather_streams=args.gather_streams or None)
     feat_bytes = sum(f.numel() * 4 for f in p.features)
 
     sampler = ClockSampler(torch.cuda.current_device() if "CUDA_VISIBLE_DEVICES" not in os.environ

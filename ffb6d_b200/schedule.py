@@ -134,7 +134,7 @@ def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
 
 
 def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None,
-                        pyramid=None, image_hw=None, events=None):
+                        pyramid=None, image_hw=None, events=None, priority=None):
     """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
 
     :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
@@ -142,6 +142,9 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
       pass ``pyramid={2: [B,HW/4,3], 4: ..., 8: ...}`` + ``image_hw=(H, W)`` (what
       :func:`ffb6d_b200.ops.backproject` returns) and leave it None
     :param streams: optional list of side ``torch.cuda.Stream`` s to overlap the 22 searches on
+    :param priority: optional ``{index key: float}``; with ``streams`` the searches (and the grid
+      builds they need) are issued in descending priority instead of descending size, so that the
+      searches whose consumers are expensive finish first
     :param events: optional dict; with ``streams`` it receives one ``torch.cuda.Event`` per index
       key, recorded on the side stream that produced it, and the function returns WITHOUT joining
       the side streams: the caller waits per key (``stream.wait_event``) and joins ``streams``
@@ -208,7 +211,16 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     fork()
     # a search waits only for ITS grid, a consumer only for ITS index tensor (events, not joins)
     built = {}
-    for i, g in enumerate(sorted(gridded, key=lambda g: -sets[g[0]].shape[1])):
+    if par and priority:
+        order = sorted(calls, key=lambda c: -priority.get(c[0], 0.0))
+        first_use = {}
+        for pos, (key, s_, q_, kk_) in enumerate(order):
+            first_use.setdefault((s_, kk_), pos)
+        build_order = sorted(gridded, key=lambda g: first_use.get(g, len(order)))
+    else:
+        order = sorted(calls, key=lambda c: -(sets[c[2]].shape[1] * c[3])) if par else calls
+        build_order = sorted(gridded, key=lambda g: -sets[g[0]].shape[1])
+    for i, g in enumerate(build_order):
         with on(i):
             if timer is not None:
                 timer.start("knn_build:%s%d:k%d" % (g[0][0], g[0][1], g[1]), 0)
@@ -218,7 +230,6 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             if par:
                 built[g] = torch.cuda.Event()
                 built[g].record()
-    order = sorted(calls, key=lambda c: -(sets[c[2]].shape[1] * c[3])) if par else calls
     for i, (key, s, q, kk) in enumerate(order):
         sup, qry = sets[s], sets[q]
         with on(i):
