@@ -682,7 +682,7 @@ __device__ __forceinline__ void warp_list_offer(key_t64 &mine, key_t64 cand, int
 }
 
 template <typename IdxT, bool SELF>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 5)
 grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
                         const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
                         size_t cursor_stride, const float4 *__restrict__ sorted_all,
