@@ -7,7 +7,15 @@
 //     out[co, p] = relu( scale[co] * sum_ci W[co, ci] * X[ci, p] + shift[co] ),   X = [X1; X2]
 // i.e. a dense GEMM D[Co x P] = W[Co x Ci] * X[Ci x P] with a per-row affine + ReLU epilogue.
 //
-// This kernel fuses the concat (two K ranges read from two tensors), the GEMM, BN and ReLU:
+// Three kernels live in this file:
+//   fusion_mlp_packed_kernel  the product path: weights pre-split once (ffb6d_fusion_mlp_pack) and
+//                             fetched by bulk-async copies, warp-specialised mbarrier pipeline,
+//                             16 staging warps (K > 128) or the 3-CTA/SM DIRECT variant (K <= 128)
+//   fusion_mlp_pair_kernel    opt-in (FFB6D_MLP_PAIR=1): tcgen05.mma.cta_group::2, two CTAs per MMA
+//   fusion_mlp_kernel         first generation, kept for A/B timing (FFB6D_MLP_V1=1): threads stage
+//                             both operands, one CTA-wide barrier per k-tile; described below
+//
+// All of them fuse the concat (two K ranges read from two tensors), the GEMM, BN and ReLU:
 //   * tcgen05.mma kind::tf32, M = N = 128 per CTA, accumulators in TMEM (128 lanes x 128 columns)
 //   * fp32 fidelity through 3xTF32: every fp32 operand is split into hi = tf32(x) and
 //     lo = tf32(x - hi) while it is staged, and D += Ahi*Bhi + Alo*Bhi + Ahi*Blo (the dropped lo*lo
@@ -49,12 +57,17 @@ __device__ __forceinline__ float to_tf32(float x)
     return __uint_as_float((__float_as_uint(x) + 0x1000u) & 0xFFFFE000u);
 }
 
+#ifndef FFB6D_MLP_ROUND_LO
+#define FFB6D_MLP_ROUND_LO 1   // 0: leave the low part unrounded (the tensor core truncates it): 2 ops fewer per element
+#endif
+__device__ __forceinline__ float lo_part(float d) { return FFB6D_MLP_ROUND_LO ? to_tf32(d) : d; }
+
 __device__ __forceinline__ void split4(const float4 v, float4 &hi, float4 &lo)
 {
-    hi.x = to_tf32(v.x); lo.x = to_tf32(v.x - hi.x);
-    hi.y = to_tf32(v.y); lo.y = to_tf32(v.y - hi.y);
-    hi.z = to_tf32(v.z); lo.z = to_tf32(v.z - hi.z);
-    hi.w = to_tf32(v.w); lo.w = to_tf32(v.w - hi.w);
+    hi.x = to_tf32(v.x); lo.x = lo_part(v.x - hi.x);
+    hi.y = to_tf32(v.y); lo.y = lo_part(v.y - hi.y);
+    hi.z = to_tf32(v.z); lo.z = lo_part(v.z - hi.z);
+    hi.w = to_tf32(v.w); lo.w = lo_part(v.w - hi.w);
 }
 
 // K-major, SWIZZLE_NONE shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp: SmemDescriptor)
