@@ -20,12 +20,12 @@ from .ops import (knn_search, random_sample, nearest_interpolation, gather_neigh
                   relative_pos_encoding, choose_gather, grid_sub_sampling, KnnGrid, backproject, fusion_mlp, fusion_mlp_pack, PackedWeight, fold_batchnorm,
                   att_pool)
 from . import randla  # noqa: F401
-from .schedule import (build_ffb6d_indices, build_ffb6d_indices_from_depth, knn_schedule,  # noqa: F401
+from .schedule import (build_ffb6d_indices, build_ffb6d_indices_from_depth, build_ffb6d_indices_native, knn_schedule,  # noqa: F401
                        gather_schedule)
 from .helper_tool import DataProcessing  # noqa: F401
 
 __all__ = [
     "knn_search", "random_sample", "nearest_interpolation", "gather_neighbour",
-    "relative_pos_encoding", "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack", "PackedWeight", "fold_batchnorm", "att_pool", "randla", "build_ffb6d_indices", "build_ffb6d_indices_from_depth",
+    "relative_pos_encoding", "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack", "PackedWeight", "fold_batchnorm", "att_pool", "randla", "build_ffb6d_indices", "build_ffb6d_indices_from_depth", "build_ffb6d_indices_native",
     "knn_schedule", "gather_schedule", "DataProcessing",
 ]

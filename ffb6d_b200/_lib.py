@@ -48,6 +48,8 @@ def _load():
         "ffb6d_knn_grid_query_bytes": (sz, [i64, i64]),
         "ffb6d_knn_grid_build": (ci, [vp, i64, i64, ci, vp, sz, vp]),
         "ffb6d_knn_grid_query": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp, sz, vp]),
+        "ffb6d_build_indices_workspace_bytes": (sz, [i64, i64, i64, i64, ci]),
+        "ffb6d_build_indices": (ci, [vp, vp, vp, vp, i64, i64, i64, i64, ci, vp, ci, vp, sz, vp]),
         "ffb6d_knn_grid_tune": (None, [fp, ci]),
         "ffb6d_knn_grid_tune_k1": (None, [fp]),
         "ffb6d_knn_batch_host": (ci, [vp, sz, sz, sz, vp, sz, sz, vp]),

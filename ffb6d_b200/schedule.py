@@ -261,6 +261,44 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     return inputs
 
 
+def build_ffb6d_indices_native(cld, pyramid, image_hw, k=K_NEIGH, index_dtype=torch.int32):
+    """:func:`build_ffb6d_indices` through the single C entry point ``ffb6d_build_indices`` (one call,
+    one stream, caller-owned buffers): what a non-Python host of the library would run.  Same keys,
+    shapes, dtypes and bits as :func:`build_ffb6d_indices`.
+
+    :param cld: ``[B, N0, 3]`` float32 CUDA; :param pyramid: ``{2: [B,HW/4,3], 4: ..., 8: ...}``
+    :param image_hw: ``(H, W)`` of the full-resolution image"""
+    import ctypes
+    from ._lib import lib, check
+    from .ops import _stream
+    if cld.dim() != 3 or cld.shape[2] != 3 or not cld.is_cuda:
+        raise ValueError("expected cld [B,N,3] on a CUDA device")
+    cld = cld.contiguous().float()
+    B, n0, _ = cld.shape
+    H, W = image_hw
+    img = {sr: pyramid[sr].contiguous().float() for sr in (2, 4, 8)}
+    for sr in (2, 4, 8):
+        if tuple(img[sr].shape) != (B, (H // sr) * (W // sr), 3):
+            raise ValueError("pyramid[%d] must be [B, %d, 3]" % (sr, (H // sr) * (W // sr)))
+    calls = knn_schedule(n0, H, W, k)
+    inputs, ptrs = {}, (ctypes.c_void_p * len(calls))()
+    for j, (key, s, q, kk) in enumerate(calls):
+        inputs[key] = torch.empty((B, set_size(q, n0, H, W), kk), dtype=index_dtype, device=cld.device)
+        ptrs[j] = inputs[key].data_ptr()
+    nbytes = int(lib.ffb6d_build_indices_workspace_bytes(B, n0, H, W, int(k)))
+    ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=cld.device)
+    with torch.cuda.device(cld.device):
+        check(lib.ffb6d_build_indices(cld.data_ptr(), img[2].data_ptr(), img[4].data_ptr(), img[8].data_ptr(), B, n0, H, W,
+                                      int(k), ctypes.cast(ptrs, ctypes.c_void_p), int(index_dtype == torch.int64),
+                                      ws.data_ptr(), nbytes, _stream(cld.device)))
+    n = n0
+    for i in range(N_DS_LAYERS):
+        inputs["cld_xyz%d" % i] = cld if i == 0 else cld[:, :n, :].contiguous()
+        n //= PCLD_SUB_S_R[i]
+        inputs["cld_sub_idx%d" % i] = inputs["cld_nei_idx%d" % i][:, :n, :].contiguous()
+    return inputs
+
+
 def build_ffb6d_indices_from_depth(depth, K, choose, k=K_NEIGH, index_dtype=torch.int32, streams=None):
     """Depth map in, all index tensors out: back-projection, sampling and stride pyramids
     (datasets/ycb/ycb_dataset.py:165-176, 237, 253-267) followed by the 22 searches, everything on

@@ -112,6 +112,25 @@ int ffb6d_knn_grid_query(const float *support, const float *query,
                          const void *grid, size_t grid_bytes,
                          void *scratch, size_t scratch_bytes, ffb6d_stream_t stream);
 
+/*
+ * The whole index build of a batch in one call: the 22 searches of datasets/ycb/ycb_dataset.py:269-309
+ * (== datasets/linemod/linemod_dataset.py:313-353) on `stream`, one grid per (support set, K class).
+ *   cld  [B,N0,3]: the sampled, shuffled clouds; level i of the pyramid = the first N0/4^i rows (:278)
+ *   img2/img4/img8 [B,(H/sr)*(W/sr),3]: stride-sr sub-grids of the organised cloud (:253-267;
+ *                  ffb6d_backproject writes them), zero rows at holes
+ *   out[22]: device buffers in the reference's call order -- for i = 0..3: cld_nei_idx{i} [B,N_i,K],
+ *            cld_interp_idx{i} [B,N_i,1], r2p_ds_nei_idx{i} [B,N_{i+1},K], p2r_ds_nei_idx{i} [B,HW(sr_i),1]
+ *            (sr = 4,8,8,8); then for i = 0..2: r2p_up_nei_idx{i} [B,N_{3-i},K], p2r_up_nei_idx{i}
+ *            [B,HW(sr_i),1] (sr = 4,2,2); int32, or int64 with idx_is_i64.  cld_sub_idx{i} is the
+ *            first N_{i+1} rows of cld_nei_idx{i} (:279).
+ * N0 a multiple of 256, H and W multiples of 8.  workspace: ffb6d_build_indices_workspace_bytes.
+ */
+size_t ffb6d_build_indices_workspace_bytes(int64_t B, int64_t N0, int64_t H, int64_t W, int K);
+int ffb6d_build_indices(const float *cld, const float *img2, const float *img4, const float *img8,
+                        int64_t B, int64_t N0, int64_t H, int64_t W, int K,
+                        void *const *out, int idx_is_i64, void *workspace, size_t workspace_bytes,
+                        ffb6d_stream_t stream);
+
 /* Performance knobs of the grid search (never affect results): the cell edge is
  * cell_scale x the `quantile`-th smallest (0..31) of 32 sampled K-th-neighbour distances.
  * Non-positive / negative arguments leave a knob unchanged.  Defaults 1.0 and 17. */

@@ -130,6 +130,37 @@ def test_schedule_digest_full_frame(cuda, frame):
         assert torch.equal(inputs["cld_sub_idx%d" % i], inputs["cld_nei_idx%d" % i][:, : n // 4])
 
 
+@pytest.mark.parametrize("dtype", [torch.int32, torch.int64])
+def test_native_schedule_entry_point(cuda, dtype):
+    """ffb6d_build_indices (one C call, caller-owned buffers and workspace) == the reference's 22 arrays
+    for a full frame (golden sha256) and == the Python scheduler on a second, batched input."""
+    from ffb6d_b200.schedule import image_pyramid
+    from ffb6d_b200.synthetic import make_frame, make_batch
+    d = json.load(open(os.path.join(GOLDEN, "schedule_digest.json")))["frames"]["seed0_n12288"]
+    fr = make_frame(d["seed"], n_points=d["n_points"])
+    cld = torch.from_numpy(fr["cld"])[None].cuda()
+    xyz = torch.from_numpy(fr["dpt_xyz"])[None].cuda()
+    pyr = image_pyramid(xyz, (2, 4, 8))
+    got = F.build_ffb6d_indices_native(cld, pyr, xyz.shape[1:3], index_dtype=dtype)
+    for key, meta in d["keys"].items():
+        g = got[key][0].cpu().numpy()
+        assert g.dtype == (np.int32 if dtype == torch.int32 else np.int64) and list(g.shape) == meta["shape"], key
+        assert hashlib.sha256(np.ascontiguousarray(g.astype(np.int32)).tobytes()).hexdigest() == meta["sha256"], key
+    batch = make_batch(range(40, 43), n_points=3072)
+    cld = torch.from_numpy(batch["cld"]).cuda()
+    xyz = torch.from_numpy(batch["dpt_xyz"]).cuda()
+    want = F.build_ffb6d_indices(cld, xyz, index_dtype=dtype)
+    got = F.build_ffb6d_indices_native(cld, image_pyramid(xyz, (2, 4, 8)), xyz.shape[1:3], index_dtype=dtype)
+    assert set(got) == set(want)
+    for key in want:
+        assert torch.equal(got[key], want[key]), key
+    # error behaviour: short workspace / bad sizes are reported, not executed
+    from ffb6d_b200._lib import lib
+    assert lib.ffb6d_build_indices_workspace_bytes(1, 100, 480, 640, 16) == 0
+    with pytest.raises(Exception):
+        F.build_ffb6d_indices_native(cld[:, :1000], image_pyramid(xyz, (2, 4, 8)), xyz.shape[1:3])
+
+
 def test_schedule_properties_at_full_batch(cuda):
     """BASELINE config 2 sizes (B=32 is sharded here as 4 frames to bound memory/time of the
     CPU checks): size-independent properties of every one of the 22 index tensors."""
