@@ -84,3 +84,32 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", text, flags=re.M), f
                 assert "liboracle" not in text and "_ref/" not in text, f
+
+
+def test_schedule_and_mlp_planning_need_no_gpu():
+    """Host-side arithmetic of the one-call schedule and the packed-weight layout; argument errors are
+    reported before any CUDA call."""
+    lib = _lib.lib
+    # 32 KB ([A_hi | A_lo], 128 rows x 32 k) per (row tile, k-tile)
+    assert lib.ffb6d_fusion_mlp_pack_bytes(1024, 2048) == 8 * 64 * 32768
+    assert lib.ffb6d_fusion_mlp_pack_bytes(70, 44) == 1 * 2 * 32768          # ragged sizes round up
+    assert lib.ffb6d_fusion_mlp_pack_bytes(0, 16) == 0
+    w1 = lib.ffb6d_build_indices_workspace_bytes(1, 12288, 480, 640, 16)
+    w4 = lib.ffb6d_build_indices_workspace_bytes(4, 12288, 480, 640, 16)
+    assert 0 < w1 < w4 <= 4 * w1 + 4096
+    assert lib.ffb6d_build_indices_workspace_bytes(1, 100, 480, 640, 16) == 0     # N0 too small
+    assert lib.ffb6d_build_indices_workspace_bytes(1, 12288, 480, 640, 65) == 0   # K too large
+    one = (C.c_float * 3)(0, 0, 0)
+    p = C.addressof(one)
+    outs = (C.c_void_p * 22)(*([p] * 22))
+    args = (p, p, p, p)
+    assert lib.ffb6d_build_indices(*args, 1, 1000, 480, 640, 16, outs, 0, p, 1 << 30, None) == _lib.ERR_INVALID
+    assert "multiple of 256" in _lib.last_error()
+    assert lib.ffb6d_build_indices(*args, 1, 12288, 481, 640, 16, outs, 0, p, 1 << 30, None) == _lib.ERR_INVALID
+    assert lib.ffb6d_build_indices(*args, 1, 12288, 480, 640, 16, outs, 0, p, 16, None) == _lib.ERR_WORKSPACE
+    assert lib.ffb6d_build_indices(*args, 0, 12288, 480, 640, 16, outs, 0, p, 0, None) == _lib.OK   # empty batch
+    outs[5] = None
+    assert lib.ffb6d_build_indices(*args, 1, 12288, 480, 640, 16, outs, 0, p, 1 << 30, None) == _lib.ERR_INVALID
+    assert "out[5]" in _lib.last_error()
+    assert lib.ffb6d_fusion_mlp_pack(None, 64, 64, p, 1 << 20, None) == _lib.ERR_INVALID
+    assert lib.ffb6d_fusion_mlp_pack(p, 64, 64, p, 16, None) == _lib.ERR_WORKSPACE
