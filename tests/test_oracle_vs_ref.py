@@ -29,6 +29,24 @@ def test_knn_surface_frame():
     assert np.array_equal(O.knn_batch(cld, cld, 16), R.knn_batch(cld, cld, 16))
 
 
+@pytest.mark.parametrize("n_points", [4096, 40960, 131072])
+def test_knn_stress_sweep_sizes(n_points):
+    """BASELINE configs[4] sizes: the port still equals the reference's KD-tree on the big clouds
+    (self search K = 16 on level 1, image -> cloud K = 1 and cloud -> image K = 32 on level 2)."""
+    from ffb6d_b200.synthetic import make_frame
+    fr = make_frame(21, n_points=n_points)
+    lvl1 = fr["cld"][None, : n_points // 4]
+    lvl2 = fr["cld"][None, : n_points // 16]
+    img = np.ascontiguousarray(fr["dpt_xyz"][::4, ::4].reshape(1, -1, 3))
+    # dense clouds do produce the odd exact fp32 distance tie (seen: one row of 10240 at N0 = 40960), and
+    # the hole pixels of the image level are exact duplicates: rows may then differ in ORDER only
+    for sup, qry, k in ((lvl1, lvl1, 16), (lvl2, img, 1), (img, lvl2, 32)):
+        got, want = O.knn_batch(sup, qry, k), R.knn_batch(sup, qry, k)
+        ok, ndiff, nties, msg = O.knn_matches(sup, qry, got, want)
+        assert ok and ndiff == nties, msg
+        assert ndiff <= max(4, got.shape[1] // 1000) or sup is img, msg
+
+
 def test_torch_ops_random():
     import torch
     f = R.torch_functions()
