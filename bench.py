@@ -8,9 +8,10 @@ A *step* is one pass of the hot path over one batch of synthetic frames: the 22 
 builds of the dataset schedule + the 23 gathers of FFB6D.forward, B frames
 per GPU (default 32 = BASELINE.json configs[1]).  metric = points/sec = GPUs * B * N0 / t_pass.
 
-One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the step's xyz
-inputs come from pinned host memory (H2D inside the timed region) and a result digest is read
-back (D2H inside).  `roofline`: the dominant kernel, per-op CUDA events on the launching stream
+One JSON line on stdout (rank 0).  `value`: inputs resident in HBM.  `e2e`: the step's depth maps
+and `choose` indices come from pinned host memory (H2D inside the timed region), are back-projected
+on the device, and a result digest is read back (D2H inside).  Other flags: --batch, --n-points, --k
+(stress sweep), --layout, --streams / --gather-streams (graph branches), --no-graph, --per-op.  `roofline`: the dominant kernel, per-op CUDA events on the launching stream
 inside the timed region, against MEASURED_PEAKS.json.  `cpu_baseline`: the reference's compiled
 KNN (oracle/_ref, nanoflann, OpenMP over the batch) + its torch gather expression on the host
 cores, bounded sample.
