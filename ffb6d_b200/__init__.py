@@ -11,21 +11,41 @@ Public surface (same names and argument meaning as the reference, ethnhe/FFB6D):
 * :func:`grid_sub_sampling` -- ``DataProcessing.grid_sub_sampling`` (helper_tool.py:199-219)
 * :func:`build_ffb6d_indices` -- the 22-call KNN schedule of the datasets
   (datasets/ycb/ycb_dataset.py:269-309) run on the GPU in one go.
+* :mod:`ffb6d_b200.modules` -- ``nn.Module`` twins of the fusion ``Conv2d`` and of RandLA's
+  ``Att_pooling`` / ``Building_block`` / ``Dilated_res_block`` (reference parameter names).
 
 Everything runs through libffb6d_b200.so (hand-written CUDA behind a C ABI, see
-include/ffb6d_b200.h); there is no CPU fallback.
+include/ffb6d_b200.h); there is no CPU fallback: touching any op loads the library and raises if
+it is missing.  Only the plain-data helpers (:mod:`ffb6d_b200.tables`, :mod:`ffb6d_b200.synthetic`)
+are importable without it -- that is what lets the CPU reference arm of ``bench.py`` run without
+mapping the product library.
 """
-from . import _lib  # noqa: F401  (raises if the CUDA library is not built)
-from .ops import (knn_search, random_sample, nearest_interpolation, gather_neighbour,  # noqa: F401
-                  relative_pos_encoding, choose_gather, grid_sub_sampling, KnnGrid, backproject, fusion_mlp, fusion_mlp_pack, PackedWeight, fold_batchnorm,
-                  att_pool)
-from . import randla  # noqa: F401
-from .schedule import (build_ffb6d_indices, build_ffb6d_indices_from_depth, build_ffb6d_indices_native, knn_schedule,  # noqa: F401
-                       gather_schedule)
-from .helper_tool import DataProcessing  # noqa: F401
+import importlib
 
-__all__ = [
-    "knn_search", "random_sample", "nearest_interpolation", "gather_neighbour",
-    "relative_pos_encoding", "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack", "PackedWeight", "fold_batchnorm", "att_pool", "randla", "build_ffb6d_indices", "build_ffb6d_indices_from_depth", "build_ffb6d_indices_native",
-    "knn_schedule", "gather_schedule", "DataProcessing",
-]
+_OPS = ("knn_search", "random_sample", "nearest_interpolation", "gather_neighbour", "relative_pos_encoding",
+        "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack",
+        "PackedWeight", "fold_batchnorm", "att_pool")
+_SCHEDULE = ("build_ffb6d_indices", "build_ffb6d_indices_from_depth", "build_ffb6d_indices_native")
+_TABLES = ("knn_schedule", "gather_schedule", "fusion_mlp_schedule")
+_SUBMODULES = ("ops", "schedule", "tables", "synthetic", "pipeline", "randla", "modules", "fusion", "dist",
+               "helper_tool", "_lib")
+
+__all__ = list(_OPS + _SCHEDULE + _TABLES) + ["randla", "modules", "fusion", "DataProcessing"]
+
+
+def __getattr__(name):   # PEP 562: the CUDA library is loaded by the first op that is touched
+    if name in _OPS:
+        return getattr(importlib.import_module(".ops", __name__), name)
+    if name in _SCHEDULE:
+        return getattr(importlib.import_module(".schedule", __name__), name)
+    if name in _TABLES:
+        return getattr(importlib.import_module(".tables", __name__), name)
+    if name == "DataProcessing":
+        return importlib.import_module(".helper_tool", __name__).DataProcessing
+    if name in _SUBMODULES:
+        return importlib.import_module("." + name, __name__)
+    raise AttributeError("module %r has no attribute %r" % (__name__, name))
+
+
+def __dir__():
+    return sorted(set(globals()) | set(__all__))

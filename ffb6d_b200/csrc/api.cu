@@ -6,6 +6,7 @@
 #include <atomic>
 #include <mutex>
 #include <string.h>
+#include <stdlib.h>
 
 namespace ffb6d {
 
@@ -20,6 +21,58 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+
+int current_device()
+{
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) {
+        cudaGetLastError();
+        dev = 0;
+    }
+    return dev;
+}
+
+const DeviceInfo &device_info()
+{
+    static DeviceInfo info[kMaxDevices];
+    static std::atomic<unsigned long long> known{0};
+    const int dev = current_device() & (kMaxDevices - 1);
+    if (!((known.load(std::memory_order_acquire) >> dev) & 1ull)) {
+        DeviceInfo d;
+        if (cudaDeviceGetAttribute(&d.num_sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || d.num_sms < 1) {
+            cudaGetLastError();
+            d.num_sms = 148;   // B200
+        }
+        if (cudaDeviceGetAttribute(&d.max_smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
+            cudaGetLastError();
+            d.max_smem_optin = 48 * 1024;
+        }
+        info[dev] = d;   // racing threads write identical values
+        known.fetch_or(1ull << dev, std::memory_order_release);
+    }
+    return info[dev];
+}
+
+const Env &env()
+{
+    static const Env e = [] {
+        Env v;
+        auto on = [](const char *n) { const char *x = getenv(n); return x && *x && strcmp(x, "0") != 0; };
+        v.gather_direct = on("FFB6D_GATHER_DIRECT");
+        v.mlp_no_direct = on("FFB6D_MLP_NO_DIRECT");
+        v.mlp_pair = on("FFB6D_MLP_PAIR");
+        v.check_indices = on("FFB6D_CHECK_INDICES");
+        v.grid_thread_search = on("FFB6D_GRID_THREAD_SEARCH");
+        const char *x;
+        v.grid_scale = (x = getenv("FFB6D_GRID_SCALE")) ? (float)atof(x) : 1.0f;
+        v.grid_scale_k1 = (x = getenv("FFB6D_GRID_SCALE_K1")) ? (float)atof(x) : 2.5f;
+        v.grid_quantile = (x = getenv("FFB6D_GRID_QUANTILE")) ? atoi(x) : 17;
+        if (v.grid_quantile < 0) v.grid_quantile = 0;
+        if (v.grid_quantile > 31) v.grid_quantile = 31;
+        return v;
+    }();
+    return e;
+}
 
 // Grow-only device scratch used ONLY by the blocking *_host entry points (the
 // device-pointer API never allocates).  One per process, guarded by a mutex:

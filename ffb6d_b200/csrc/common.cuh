@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/ffb6d_b200.h"
 
@@ -46,7 +47,41 @@ void count_launch(int n = 1);
 static inline int64_t ceil_div(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 
-constexpr int kNumSMs = 148;  // B200
+// Per-device facts, cached per device ordinal (a process may drive several GPUs: function attributes
+// and SM counts belong to the CURRENT device, never to the process).
+constexpr int kMaxDevices = 64;
+struct DeviceInfo {
+    int num_sms;          // 148 on B200
+    int max_smem_optin;   // bytes of dynamic shared memory a kernel may opt into
+};
+int current_device();                 // cudaGetDevice, 0 on error
+const DeviceInfo &device_info();      // of the current device
+static inline int num_sms() { return device_info().num_sms; }
+
+// One-time (per kernel instantiation AND per device) opt-in to more than 48 KB of dynamic shared
+// memory.  Not a stream operation, so it is safe under CUDA-graph capture.
+#define FFB6D_OPTIN_SMEM(kern, bytes)                                                              \
+    do {                                                                                           \
+        static std::atomic<unsigned long long> done__{0};                                          \
+        const int dev__ = ::ffb6d::current_device() & (::ffb6d::kMaxDevices - 1);                  \
+        if (!((done__.load(std::memory_order_relaxed) >> dev__) & 1ull)) {                         \
+            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,     \
+                                            (int)(bytes)));                                        \
+            done__.fetch_or(1ull << dev__, std::memory_order_relaxed);                             \
+        }                                                                                          \
+    } while (0)
+
+// Experiment switches, read ONCE per process (never in a launch path; results never depend on them).
+struct Env {
+    bool gather_direct;     // FFB6D_GATHER_DIRECT=1: K-lane gathers through the older direct kernel
+    bool mlp_no_direct;     // FFB6D_MLP_NO_DIRECT=1
+    bool mlp_pair;          // FFB6D_MLP_PAIR=1
+    bool check_indices;     // FFB6D_CHECK_INDICES=1: validate gather indices (synchronises; debugging aid)
+    bool grid_thread_search;
+    float grid_scale, grid_scale_k1;
+    int grid_quantile;
+};
+const Env &env();
 
 // The reference distance: nanoflann L2_Adaptor::evalMetric tail loop for dim 3
 // (NN/nanoflann.hpp:343-346): result = 0; result += d0*d0; += d1*d1; += d2*d2 in fp32,

@@ -7,13 +7,11 @@
 //     out[co, p] = relu( scale[co] * sum_ci W[co, ci] * X[ci, p] + shift[co] ),   X = [X1; X2]
 // i.e. a dense GEMM D[Co x P] = W[Co x Ci] * X[Ci x P] with a per-row affine + ReLU epilogue.
 //
-// Three kernels live in this file:
+// Kernels in this file:
 //   fusion_mlp_packed_kernel  the product path: weights pre-split once (ffb6d_fusion_mlp_pack) and
 //                             fetched by bulk-async copies, warp-specialised mbarrier pipeline,
 //                             16 staging warps (K > 128) or the 3-CTA/SM DIRECT variant (K <= 128)
 //   fusion_mlp_pair_kernel    opt-in (FFB6D_MLP_PAIR=1): tcgen05.mma.cta_group::2, two CTAs per MMA
-//   fusion_mlp_kernel         first generation, kept for A/B timing (FFB6D_MLP_V1=1): threads stage
-//                             both operands, one CTA-wide barrier per k-tile; described below
 //
 // All of them fuse the concat (two K ranges read from two tensors), the GEMM, BN and ReLU:
 //   * tcgen05.mma kind::tf32, M = N = 128 per CTA, accumulators in TMEM (128 lanes x 128 columns)
@@ -44,7 +42,6 @@ constexpr int TM = 128, TN = 128, TK = 32;            // CTA tile
 constexpr int CHUNK_BYTES = TM * 16;                  // one 16-byte K chunk of all 128 rows
 constexpr int TILE_BYTES = (TK / 4) * CHUNK_BYTES;    // 16 KB
 constexpr int STAGE_BYTES = 4 * TILE_BYTES;           // A_hi, A_lo, B_hi, B_lo
-constexpr int MLP_SMEM = 2 * STAGE_BYTES + 64;        // + barriers / tmem pointer
 constexpr int CH = 4;                                 // k-tiles per accumulation chunk (K = 128)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -100,214 +97,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         if (spin > (1 << 26)) __trap();   // never hang the GPU on a protocol bug
     }
 }
-
-__global__ void __launch_bounds__(256, 1)
-fusion_mlp_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
-                  const float *__restrict__ w, const float *__restrict__ scale,
-                  const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
-                  float slope)
-{
-    extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE_BYTES);   // [0],[1]: stage free; [2],[3]: chunk done
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE_BYTES + 48);
-    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.z, m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
-    const int Ci = C1 + C2;
-    const float *xb1 = x1 + (size_t)b * C1 * P;
-    const float *xb2 = x2 ? x2 + (size_t)b * C2 * P : nullptr;
-
-    if (wid == 0) {   // TMEM: two accumulators of 128 fp32 columns
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(2 * TN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-    }
-    if (tid == 32) {
-        for (int i = 0; i < 4; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)));
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const uint32_t tmem_d = *tmem_slot;
-
-    // 128-bit paths: weights need Ci % 4 == 0, activations / outputs need P % 4 == 0 (and aligned bases)
-    const bool vecA = ((Ci & 3) == 0) && ((reinterpret_cast<uintptr_t>(w) & 15) == 0);
-    const bool vec = ((P & 3) == 0) && ((reinterpret_cast<uintptr_t>(xb1) & 15) == 0) &&
-                     (!xb2 || (reinterpret_cast<uintptr_t>(xb2) & 15) == 0) &&
-                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-    const int nk = (Ci + TK - 1) / TK;
-    const int q = wid & 3, half = wid >> 2;   // this thread's accumulator row = 32q + lane, columns 64*half ..
-    float acc[64];
-#pragma unroll
-    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
-    // add chunk `c`'s TMEM accumulator (round-to-nearest) into the register sums
-    auto drain = [&](int c) {
-        const int buf = c & 1;
-        mbar_wait(smem_u32(bars + 2 + buf), (uint32_t)((c >> 1) & 1));
-        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-#pragma unroll
-        for (int i = 0; i < 2; ++i) {
-            uint32_t v[32];
-            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + 64 * half + 32 * i);
-            asm volatile(
-                "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-                "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
-                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
-                  "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
-                  "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-                : "r"(taddr));
-            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc[32 * i + j] = __fadd_rn(acc[32 * i + j], __uint_as_float(v[j]));
-        }
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    };
-    // global -> registers: A = W[m0.., k0..] (128 rows x 8 chunks, 4 chunks per thread) and
-    // B = X[k0.., n0..] (one 4(k) x 4(n) block per thread)
-    auto load_tile = [&](int kt, float4 (&ra)[4], float4 (&rb)[4]) {
-        const int k0 = kt * TK;
-        // warp w stages K chunk w; lanes take consecutive rows so the 16-byte shared-memory stores of a
-        // warp are contiguous (bank-conflict free); W is small and L2-resident, the strided reads are cheap
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = lane + 32 * i, c = wid;
-            const int gm = m0 + m, gk = k0 + 4 * c;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gm < Co) {
-                const float *src = w + (size_t)gm * Ci + gk;
-                if (vecA && gk + 3 < Ci) {
-                    v = __ldg(reinterpret_cast<const float4 *>(src));
-                } else {
-                    if (gk + 0 < Ci) v.x = __ldg(src + 0);
-                    if (gk + 1 < Ci) v.y = __ldg(src + 1);
-                    if (gk + 2 < Ci) v.z = __ldg(src + 2);
-                    if (gk + 3 < Ci) v.w = __ldg(src + 3);
-                }
-            }
-            ra[i] = v;
-        }
-        const int kg = tid >> 5, ng = tid & 31;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int gk = k0 + 4 * kg + j, gn = n0 + 4 * ng;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (gk < Ci) {
-                const float *row = (gk < C1) ? xb1 + (size_t)gk * P : xb2 + (size_t)(gk - C1) * P;
-                if (vec && gn + 3 < P) {
-                    v = __ldg(reinterpret_cast<const float4 *>(row + gn));
-                } else {
-                    if (gn + 0 < P) v.x = __ldg(row + gn + 0);
-                    if (gn + 1 < P) v.y = __ldg(row + gn + 1);
-                    if (gn + 2 < P) v.z = __ldg(row + gn + 2);
-                    if (gn + 3 < P) v.w = __ldg(row + gn + 3);
-                }
-            }
-            rb[j] = v;
-        }
-    };
-    // registers -> hi/lo split -> shared memory in the UMMA K-major layout (X transposed on the way)
-    auto store_tile = [&](int st, const float4 (&ra)[4], const float4 (&rb)[4]) {
-        unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
-        unsigned char *sB_hi = sA_lo + TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
-        float4 hi, lo;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int m = lane + 32 * i, c = wid;
-            split4(ra[i], hi, lo);
-            *reinterpret_cast<float4 *>(sA_hi + c * CHUNK_BYTES + m * 16) = hi;
-            *reinterpret_cast<float4 *>(sA_lo + c * CHUNK_BYTES + m * 16) = lo;
-        }
-        const int kg = tid >> 5, ng = tid & 31;
-        const float4 t0 = make_float4(rb[0].x, rb[1].x, rb[2].x, rb[3].x);   // n = 4ng + 0, k = 4kg .. 4kg+3
-        const float4 t1 = make_float4(rb[0].y, rb[1].y, rb[2].y, rb[3].y);
-        const float4 t2 = make_float4(rb[0].z, rb[1].z, rb[2].z, rb[3].z);
-        const float4 t3 = make_float4(rb[0].w, rb[1].w, rb[2].w, rb[3].w);
-        unsigned char *bh = sB_hi + kg * CHUNK_BYTES + (4 * ng) * 16, *bl = sB_lo + kg * CHUNK_BYTES + (4 * ng) * 16;
-        // a lane owns four consecutive 16-byte slots (64-byte lane stride): rotating which slot each
-        // lane writes per instruction makes every quarter-warp cover all 32 banks
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const int x = (i + (ng >> 1)) & 3;
-            const float4 tx = (x == 0) ? t0 : (x == 1) ? t1 : (x == 2) ? t2 : t3;
-            split4(tx, hi, lo);
-            *reinterpret_cast<float4 *>(bh + 16 * x) = hi;
-            *reinterpret_cast<float4 *>(bl + 16 * x) = lo;
-        }
-    };
-
-    float4 ra[4], rb[4], na[4], nb[4];
-    load_tile(0, ra, rb);
-    for (int kt = 0; kt < nk; ++kt) {
-        const int st = kt & 1;
-        unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
-        unsigned char *sB_hi = sA_lo + TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
-        // the next tile's global loads are in flight while this one is split, stored and multiplied
-        if (kt + 1 < nk) load_tile(kt + 1, na, nb);
-        if (kt >= 2) mbar_wait(smem_u32(bars + st), ((kt >> 1) - 1) & 1);   // MMAs that read this stage are done
-        store_tile(st, ra, rb);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        __syncthreads();
-        if (tid == 0) {
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const uint32_t a_hi = smem_u32(sA_hi), a_lo = smem_u32(sA_lo), b_hi = smem_u32(sB_hi), b_lo = smem_u32(sB_lo);
-            const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
-            for (int j = 0; j < TK / 8; ++j) {   // one MMA consumes K = 8 (two 16-byte chunks)
-                const uint32_t off = j * 2 * CHUNK_BYTES;
-                umma_tf32(d_buf, umma_desc(a_hi + off), umma_desc(b_hi + off), (kt % CH != 0 || j > 0) ? 1u : 0u);
-                umma_tf32(d_buf, umma_desc(a_lo + off), umma_desc(b_hi + off), 1u);
-                umma_tf32(d_buf, umma_desc(a_hi + off), umma_desc(b_lo + off), 1u);
-            }
-            // arrive on this stage's barrier when the MMAs issued so far have completed
-            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                         :: "r"(smem_u32(bars + st)) : "memory");
-            if (kt % CH == CH - 1 || kt == nk - 1)   // ... and on the chunk's barrier when a chunk ends
-                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
-                             :: "r"(smem_u32(bars + 2 + ((kt / CH) & 1))) : "memory");
-        }
-        // the previous chunk is drained while the tensor core works on this one
-        if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {   // the prefetched tile becomes the current one
-            ra[i] = na[i];
-            rb[i] = nb[i];
-        }
-    }
-    drain((nk - 1) / CH);
-    // ---- epilogue: register sums -> scale/shift/ReLU -> global
-    {
-        const int gm = m0 + 32 * q + lane;
-        if (gm < Co) {
-            const float sc = __ldg(scale + gm), sh = __ldg(shift + gm);
-            float *orow = out + ((size_t)b * Co + gm) * P;
-#pragma unroll
-            for (int j = 0; j < 64; j += 4) {
-                const int gn = n0 + 64 * half + j;
-                float y[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    // BN(eval) folded: y = conv * scale + shift, unfused like torch's affine
-                    y[u] = __fadd_rn(__fmul_rn(acc[j + u], sc), sh);
-                    if (act == 1) y[u] = fmaxf(y[u], 0.f);
-                    else if (act == 2) y[u] = (y[u] > 0.f) ? y[u] : __fmul_rn(y[u], slope);   // LeakyReLU
-                }
-                if (vec && gn + 3 < P) {
-                    *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (gn + u < P) orow[gn + u] = y[u];
-                }
-            }
-        }
-    }
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(2 * TN));
-}
-
 
 // ===================================================================== packed-weight kernel
 // The weights are constants at inference: their hi/lo split is computed once
@@ -932,25 +721,19 @@ extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const fl
 {
     const int rc = mlp_check(x1, C1, x2, C2, packed, scale, shift, B, Co, P, act, out);
     if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
-    static bool optin_done = false;
-    if (!optin_done) {
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<3, false, 16, 3>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(3)));
-        FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_packed_kernel<1, true, 8, 2>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, mlp2_smem(1)));
-        optin_done = true;
+    {
+        auto k_big = fusion_mlp_packed_kernel<3, false, 16, 3>;
+        auto k_direct = fusion_mlp_packed_kernel<1, true, 8, 2>;
+        FFB6D_OPTIN_SMEM(k_big, mlp2_smem(3));
+        FFB6D_OPTIN_SMEM(k_direct, mlp2_smem(1));
     }
     dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
-    static const bool no_direct = getenv("FFB6D_MLP_NO_DIRECT") != nullptr;
+    const bool no_direct = env().mlp_no_direct;
     // opt-in (FFB6D_MLP_PAIR=1): validated, but at present ~10 % slower than the single-CTA kernel on the
     // large layers (cluster-scope barrier round trips per stage)
-    static const bool pair = getenv("FFB6D_MLP_PAIR") != nullptr;
+    const bool pair = env().mlp_pair;
     if (pair && grid.y % 2 == 0 && grid.x <= 65535 && ceil_div(C1 + C2, TK) > CH) {
-        static bool pair_optin = false;
-        if (!pair_optin) {
-            FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PAIR_SMEM));
-            pair_optin = true;
-        }
+        FFB6D_OPTIN_SMEM(fusion_mlp_pair_kernel, PAIR_SMEM);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid.y, grid.x, grid.z);   // x = 128-row tile of W (pairs), y = 128-column tile of X
         cfg.blockDim = dim3(PAIR_THREADS);
@@ -966,6 +749,7 @@ extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const fl
         FFB6D_CUDA(cudaLaunchKernelEx(&cfg, fusion_mlp_pair_kernel, x1, (int)C1, (const float *)(C2 ? x2 : nullptr), (int)C2,
                                       (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P, act,
                                       negative_slope));
+        count_launch();
         return FFB6D_OK;
     }
     if (ceil_div(C1 + C2, TK) <= CH && !no_direct)
@@ -986,31 +770,18 @@ extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2
 {
     const int rc = mlp_check(x1, C1, x2, C2, weight, scale, shift, B, Co, P, act, out);
     if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
-    static const bool v1 = getenv("FFB6D_MLP_V1") != nullptr;   // the first-generation kernel (threads stage W too)
-    if (v1) {
-        static bool optin_done = false;
-        if (!optin_done) {
-            FFB6D_CUDA(cudaFuncSetAttribute(fusion_mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, MLP_SMEM));
-            optin_done = true;
-        }
-        dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
-        fusion_mlp_kernel<<<grid, 256, MLP_SMEM, (cudaStream_t)stream>>>(x1, (int)C1, C2 ? x2 : nullptr, (int)C2, weight,
-                                                                        scale, shift, out, (int)Co, (int)P, act,
-                                                                        negative_slope);
-        FFB6D_LAUNCH_OK("fusion_mlp_kernel");
-        return FFB6D_OK;
-    }
     // raw weights: split them into a stream-ordered scratch block first (callers that keep their
     // weights should pack once with ffb6d_fusion_mlp_pack and call ffb6d_fusion_mlp_fwd_packed)
     const size_t bytes = ffb6d_fusion_mlp_pack_bytes(Co, C1 + C2);
-    static bool pool_set = false;
-    if (!pool_set) {   // keep freed scratch blocks in the stream-ordered pool instead of returning them to the OS
+    static std::atomic<unsigned long long> pool_set_mask{0};
+    const int dev_bit = current_device() & (kMaxDevices - 1);
+    if (!((pool_set_mask.load(std::memory_order_relaxed) >> dev_bit) & 1ull)) {   // keep freed scratch blocks in the stream-ordered pool instead of returning them to the OS
         int dev = 0;
         cudaMemPool_t pool;
         unsigned long long keep = ~0ull;
         if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess)
             cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        pool_set = true;
+        pool_set_mask.fetch_or(1ull << dev_bit, std::memory_order_relaxed);
     }
     void *scratch = nullptr;
     FFB6D_CUDA(cudaMallocAsync(&scratch, bytes, (cudaStream_t)stream));

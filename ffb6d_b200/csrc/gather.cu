@@ -255,60 +255,6 @@ gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restr
     }
 }
 
-// Rows longer than shared memory with K > 1 (r2p gathers from the 240x320 map): the row is
-// streamed through shared memory in pieces; every piece updates a running maximum per query
-// (also in shared memory) with the neighbours that fall inside it.  Turns Q*K scattered
-// L1/L2 reads per row into one coalesced read of the row plus shared-memory gathers.
-template <typename IdxT, int KT>
-__global__ void __launch_bounds__(256)
-gather_max_ncs_split_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
-                            float *__restrict__ out, int C, int S, int Q, int K, int piece,
-                            int q_per_cta)
-{
-    extern __shared__ __align__(16) float sm[];
-    float *rowp = sm;            // [piece]
-    float *mx = sm + piece;      // [q_per_cta]
-    const int b = blockIdx.z, c = blockIdx.y;
-    const int q0 = blockIdx.x * q_per_cta;
-    const int nq = min(q_per_cta, Q - q0);
-    const float *src = feat + ((size_t)b * C + c) * S;
-    const IdxT *ib = idx + ((size_t)b * Q + q0) * K;
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) mx[i] = __int_as_float(0xff800000);   // -inf
-    const bool vec = ((S & 3) == 0) && ((reinterpret_cast<uintptr_t>(src) & 15) == 0);
-    for (int p0 = 0; p0 < S; p0 += piece) {
-        const int n = min(piece, S - p0);
-        __syncthreads();
-        if (vec) {   // piece and p0 are multiples of 4
-            const float4 *s4 = reinterpret_cast<const float4 *>(src + p0);
-            float4 *d4 = reinterpret_cast<float4 *>(rowp);
-            for (int t = threadIdx.x; t < (n >> 2); t += blockDim.x) d4[t] = __ldg(s4 + t);
-        } else {
-            for (int t = threadIdx.x; t < n; t += blockDim.x) rowp[t] = __ldg(src + p0 + t);
-        }
-        __syncthreads();
-        for (int i = threadIdx.x; i < nq; i += blockDim.x) {
-            float m = mx[i];
-            if constexpr (KT > 0) {
-                int id[KT];
-                load_ids<IdxT, KT>(ib + (size_t)i * K, K, id);
-#pragma unroll
-                for (int k = 0; k < KT; ++k) {
-                    const unsigned off = (unsigned)(id[k] - p0);
-                    if (off < (unsigned)n) m = max_nan(m, rowp[off]);
-                }
-            } else {
-                for (int k = 0; k < K; ++k) {
-                    const unsigned off = (unsigned)((int)__ldg(ib + (size_t)i * K + k) - p0);
-                    if (off < (unsigned)n) m = max_nan(m, rowp[off]);
-                }
-            }
-            mx[i] = m;   // slot i is only ever touched by this thread
-        }
-    }
-    float *dst = out + ((size_t)b * C + c) * Q + q0;
-    for (int i = threadIdx.x; i < nq; i += blockDim.x) dst[i] = mx[i];
-}
-
 // Long rows with K = 8/16/32 (r2p gathers from the 240x320 map): the K lanes of a group hold the K
 // neighbours of ONE query.  Neighbours of a query are adjacent pixels, so a warp-wide load touches
 // a handful of 32-byte sectors instead of 32 (lanes along the query axis would scatter every
@@ -460,17 +406,20 @@ gather_max_bwd_kernel(const float *__restrict__ feat, const IdxT *__restrict__ i
     const float g = gout[t];
     const IdxT *ip = idx + ((size_t)b * Q + q) * K;
     const float *f = feat + (size_t)b * C * S + (size_t)c * fs_c;
+    const unsigned Su = (unsigned)S;
     int best = (int)__ldg(ip);
-    float m = __ldg(f + (size_t)best * fs_s);
+    float m = __ldg(f + (size_t)min((unsigned)best, Su - 1) * fs_s);
     for (int k = 1; k < K; ++k) {
         const int s = (int)__ldg(ip + k);
-        const float v = __ldg(f + (size_t)s * fs_s);
+        const float v = __ldg(f + (size_t)min((unsigned)s, Su - 1) * fs_s);
         if ((v > m || v != v) && !(m != m)) {
             m = v;
             best = s;
         }
     }
-    atomicAdd(gfeat + (size_t)b * C * S + (size_t)c * fs_c + (size_t)best * fs_s, g);
+    // an out-of-range neighbour never writes outside grad_feat (torch.gather raises a device assert;
+    // FFB6D_CHECK_INDICES=1 / ffb6d_check_indices report it)
+    if ((unsigned)best < (unsigned)S) atomicAdd(gfeat + (size_t)b * C * S + (size_t)c * fs_c + (size_t)best * fs_s, g);
 }
 
 // ------------------------------------------------------------------ neighbour gather
@@ -509,7 +458,7 @@ gather_neighbour_bwd_kernel(const float *__restrict__ gout, const IdxT *__restri
     const int j = (int)(t % D);
     const int b = (int)(row / rows_per_b);
     const int s = (int)__ldg(idx + row);
-    atomicAdd(gpc + ((size_t)b * S + s) * D + j, gout[t]);
+    if ((unsigned)s < (unsigned)S) atomicAdd(gpc + ((size_t)b * S + s) * D + j, gout[t]);
 }
 
 // ------------------------------------------------------------------ relative position encoding
@@ -635,21 +584,47 @@ att_pool_kernel(const float *__restrict__ f1, int C1, const float *__restrict__ 
     }
 }
 
-// ------------------------------------------------------------------ host-side launch logic
-static int g_max_smem_optin = -1;
-static int max_smem_optin()
+// ------------------------------------------------------------------ index validation (debugging aid)
+// The gather kernels trust their indices (an out-of-range neighbour reads stale shared memory or a
+// foreign row where torch.gather raises a device assert).  This pass counts the offenders; it is run
+// by ffb6d_check_indices and, with FFB6D_CHECK_INDICES=1, in front of every gather entry point.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+check_indices_kernel(const IdxT *__restrict__ idx, long long n, long long S, unsigned long long *__restrict__ bad)
 {
-    if (g_max_smem_optin < 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess ||
-            cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess) {
-            cudaGetLastError();
-            v = 48 * 1024;
-        }
-        g_max_smem_optin = v;
+    unsigned long long mine = 0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const long long v = (long long)idx[t];
+        mine += (v < 0 || v >= S) ? 1ull : 0ull;
     }
-    return g_max_smem_optin;
+    if (mine) atomicAdd(bad, mine);
 }
+
+static int check_indices_sync(const void *idx, int idx_is_i64, long long n, long long S, cudaStream_t st, const char *who)
+{
+    if (n <= 0) return FFB6D_OK;
+    static unsigned long long *flag[kMaxDevices] = {nullptr};
+    const int dev = current_device() & (kMaxDevices - 1);
+    if (!flag[dev]) FFB6D_CUDA(cudaMalloc(&flag[dev], sizeof(unsigned long long)));
+    FFB6D_CUDA(cudaMemsetAsync(flag[dev], 0, sizeof(unsigned long long), st));
+    const unsigned blocks = (unsigned)std::min<long long>(ceil_div(n, 256), 4 * num_sms());
+    if (idx_is_i64)
+        check_indices_kernel<long long><<<blocks, 256, 0, st>>>((const long long *)idx, n, S, flag[dev]);
+    else
+        check_indices_kernel<int><<<blocks, 256, 0, st>>>((const int *)idx, n, S, flag[dev]);
+    FFB6D_LAUNCH_OK("check_indices_kernel");
+    unsigned long long bad = 0;
+    FFB6D_CUDA(cudaMemcpyAsync(&bad, flag[dev], sizeof(bad), cudaMemcpyDeviceToHost, st));
+    FFB6D_CUDA(cudaStreamSynchronize(st));
+    if (bad) {
+        set_error("%s: %llu of %lld indices outside [0, %lld)", who, bad, n, S);
+        return FFB6D_ERR_INVALID;
+    }
+    return FFB6D_OK;
+}
+
+// ------------------------------------------------------------------ host-side launch logic
+static int max_smem_optin() { return device_info().max_smem_optin; }
 
 template <typename IdxT, int KT>
 static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B, int64_t C,
@@ -659,10 +634,10 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
     const size_t row_bytes = (size_t)S * sizeof(float);
     // rows that fit shared memory twice over (two CTAs per SM hide the staging latency)
     const size_t budget = (size_t)smem_cap / 2;
-    const int64_t want = 4 * kNumSMs;   // CTAs to aim for
+    const int64_t want = 4 * num_sms();   // CTAs to aim for
     // few queries against long rows (Q*K gathered elements << S): staging whole rows would read far
     // more than the ~5 sectors a query's K adjacent neighbours touch per row -> K-lane gather instead
-    const bool sparse_queries = (KT == 8 || KT == 16 || KT == 32) && Q * 40 < S && !getenv("FFB6D_GATHER_DIRECT");
+    const bool sparse_queries = (KT == 8 || KT == 16 || KT == 32) && Q * 40 < S && !env().gather_direct;
     if (row_bytes <= budget && !sparse_queries) {
         int CC = (int)(budget / row_bytes);
         if (CC > C) CC = (int)C;
@@ -687,24 +662,14 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
                             ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
             if (v4) {
                 auto kern = gather1_ncs_staged_v4_kernel<IdxT>;
-                static bool optin_done = false;
-                if (!optin_done) {
-                    FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                    max_smem_optin() - 1024));
-                    optin_done = true;
-                }
+                FFB6D_OPTIN_SMEM(kern, max_smem_optin() - 1024);
                 kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, CC, (int)q_per_cta);
                 FFB6D_LAUNCH_OK("gather1_ncs_staged_v4_kernel");
                 return FFB6D_OK;
             }
         }
         auto kern = gather_max_ncs_staged_kernel<IdxT, KT>;
-        static bool optin_done = false;   // once per instantiation (not a stream op: keep it out of graphs)
-        if (!optin_done) {
-            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            max_smem_optin() - 1024));
-            optin_done = true;
-        }
+        FFB6D_OPTIN_SMEM(kern, max_smem_optin() - 1024);   // per instantiation and device; not a stream op
         kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, CC,
                                       (int)q_per_cta);
         FFB6D_LAUNCH_OK("gather_max_ncs_staged_kernel");
@@ -712,29 +677,12 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, 8), (unsigned)B);
         gather1_ncs_direct_kernel<IdxT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
         FFB6D_LAUNCH_OK("gather1_ncs_direct_kernel");
-    } else if ((KT == 8 || KT == 16 || KT == 32) && !getenv("FFB6D_GATHER_DIRECT")) {
+    } else if ((KT == 8 || KT == 16 || KT == 32) && !env().gather_direct) {
         if constexpr (KT == 8 || KT == 16 || KT == 32) {
             dim3 grid((unsigned)ceil_div(Q, 32), (unsigned)std::min<int64_t>(ceil_div(C, 8), 65535), (unsigned)B);
             gather_max_ncs_klane_kernel<IdxT, KT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
             FFB6D_LAUNCH_OK("gather_max_ncs_klane_kernel");
         }
-    } else if (C <= 65535 && getenv("FFB6D_GATHER_SPLIT")) {   // measured slower than the direct kernel on B200: opt-in
-        const int q_per_cta = (int)std::min<int64_t>(Q, 4096);
-        int piece = (int)((budget - (size_t)q_per_cta * sizeof(float)) / sizeof(float));
-        piece = piece / 1024 * 1024;
-        const int pieces = (int)ceil_div(S, piece);
-        piece = (int)(ceil_div(ceil_div(S, pieces), 1024) * 1024);   // even pieces
-        const size_t smem = ((size_t)piece + q_per_cta) * sizeof(float);
-        auto kern = gather_max_ncs_split_kernel<IdxT, KT>;
-        static bool optin_done = false;
-        if (!optin_done) {
-            FFB6D_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            max_smem_optin() - 1024));
-            optin_done = true;
-        }
-        dim3 grid((unsigned)ceil_div(Q, q_per_cta), (unsigned)C, (unsigned)B);
-        kern<<<grid, 256, smem, st>>>(feat, idx, out, (int)C, (int)S, (int)Q, K, piece, q_per_cta);
-        FFB6D_LAUNCH_OK("gather_max_ncs_split_kernel");
     } else {
         const int CC = 8;
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, CC), (unsigned)B);
@@ -781,9 +729,9 @@ const char *ffb6d_gather_kernel_name(int64_t B, int64_t C, int64_t S, int64_t Q,
     const bool fits = (size_t)S * sizeof(float) <= budget;
     if (K == 1) return fits ? ((Q % 4 == 0) ? "gather1_ncs_staged_v4_kernel" : "gather_max_ncs_staged_kernel")
                             : "gather1_ncs_direct_kernel";
-    const bool sparse_queries = (K == 8 || K == 16 || K == 32) && Q * 40 < S && !getenv("FFB6D_GATHER_DIRECT");
+    const bool sparse_queries = (K == 8 || K == 16 || K == 32) && Q * 40 < S && !env().gather_direct;
     if (fits && !sparse_queries) return "gather_max_ncs_staged_kernel";
-    if ((K == 8 || K == 16 || K == 32) && !getenv("FFB6D_GATHER_DIRECT")) return "gather_max_ncs_klane_kernel";
+    if ((K == 8 || K == 16 || K == 32) && !env().gather_direct) return "gather_max_ncs_klane_kernel";
     return "gather_max_ncs_direct_kernel";
 }
 
@@ -803,9 +751,21 @@ int ffb6d_gather_max_fwd(const float *feat, const void *idx, int idx_is_i64, int
     FFB6D_CHECK_ARG(S > 0, "gather_max_fwd: empty source with non-empty index");
     FFB6D_CHECK_ARG(feat && idx && out, "gather_max_fwd: null pointer");
     cudaStream_t st = (cudaStream_t)stream;
+    if (env().check_indices) {
+        const int rc = check_indices_sync(idx, idx_is_i64, (long long)B * Q * K, S, st, "gather_max_fwd");
+        if (rc) return rc;
+    }
     if (idx_is_i64)
         return gather_max_fwd_t<long long>(feat, (const long long *)idx, B, C, S, Q, K, layout, out, st);
     return gather_max_fwd_t<int>(feat, (const int *)idx, B, C, S, Q, K, layout, out, st);
+}
+
+int ffb6d_check_indices(const void *idx, int idx_is_i64, int64_t count, int64_t S, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(count >= 0 && S >= 0, "check_indices: negative size");
+    if (count == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(idx, "check_indices: null pointer");
+    return check_indices_sync(idx, idx_is_i64, (long long)count, (long long)S, (cudaStream_t)stream, "check_indices");
 }
 
 int ffb6d_gather_max_bwd(const float *feat, const void *idx, int idx_is_i64, const float *grad_out,
@@ -825,6 +785,10 @@ int ffb6d_gather_max_bwd(const float *feat, const void *idx, int idx_is_i64, con
     if (B == 0 || C == 0 || Q == 0) return FFB6D_OK;
     FFB6D_CHECK_ARG(S > 0, "gather_max_bwd: empty source with non-empty index");
     FFB6D_CHECK_ARG(feat && idx && grad_out, "gather_max_bwd: null pointer");
+    if (env().check_indices) {
+        const int rc = check_indices_sync(idx, idx_is_i64, (long long)B * Q * K, S, st, "gather_max_bwd");
+        if (rc) return rc;
+    }
     const long long total = (long long)B * C * Q;
     const unsigned blocks = (unsigned)ceil_div(total, 256);
     if (idx_is_i64)
@@ -848,6 +812,10 @@ int ffb6d_gather_neighbour_fwd(const float *pc, const void *idx, int idx_is_i64,
     FFB6D_CHECK_ARG(pc && idx && out, "gather_neighbour_fwd: null pointer");
     FFB6D_CHECK_ARG(S < (1ll << 31) && D < (1ll << 31), "gather_neighbour_fwd: size too large");
     cudaStream_t st = (cudaStream_t)stream;
+    if (env().check_indices) {
+        const int rc = check_indices_sync(idx, idx_is_i64, (long long)B * N * K, S, st, "gather_neighbour_fwd");
+        if (rc) return rc;
+    }
     const long long rows_per_b = (long long)N * K;
     const bool v4 = (D % 4 == 0) && ((reinterpret_cast<uintptr_t>(pc) & 15) == 0) &&
                     ((reinterpret_cast<uintptr_t>(out) & 15) == 0);

@@ -183,7 +183,7 @@ extern "C" int ffb6d_grid_subsample_host(const float *points, size_t N, const fl
                                          int *sub_classes, size_t *M_out)
 {
     FFB6D_CHECK_ARG(points && sub_points && M_out, "grid_subsample: null pointer");
-    FFB6D_CHECK_ARG(N >= 1 && N < (1ull << 32), "grid_subsample: N=%zu outside [1, 2^32)", N);
+    FFB6D_CHECK_ARG(N >= 1 && N < (1ull << 31), "grid_subsample: N=%zu outside [1, 2^31) (32-bit item counts of the sort / scan)", N);
     FFB6D_CHECK_ARG(sampleDl > 0.f, "grid_subsample: sampleDl must be positive");
     FFB6D_CHECK_ARG(fdim == 0 || (features && sub_features), "grid_subsample: null features");
     FFB6D_CHECK_ARG(ldim == 0 || (classes && sub_classes), "grid_subsample: null classes");

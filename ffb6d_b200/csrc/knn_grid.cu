@@ -965,20 +965,23 @@ grid_dup_copy_kernel(int Q, int K, const QueryState *__restrict__ state_all,
 }
 
 // ------------------------------------------------------------------ host
-static bool g_force_thread_search = false;   // FFB6D_GRID_THREAD_SEARCH=1: one thread per query for every K
+// cell-size knobs: defaults from the environment (read once, common.cuh Env), overridable by
+// ffb6d_knn_grid_tune* (tools/tune_grid.py); results never depend on them
+static bool g_force_thread_search = false;
 static float g_cell_scale = 1.0f;
 static float g_cell_scale_k1 = 2.5f;   // grids built for K = 1 searches (measured optimum 2 ... 2.8)
 static int g_quantile = 17;
-static bool g_env_read = false;
+static std::atomic<bool> g_env_read{false};
 
 static void read_env()
 {
-    if (g_env_read) return;   // tuning knobs for experiments; results never depend on them
-    if (const char *e = getenv("FFB6D_GRID_SCALE")) g_cell_scale = (float)atof(e);
-    if (const char *e = getenv("FFB6D_GRID_SCALE_K1")) g_cell_scale_k1 = (float)atof(e);
-    if (const char *e = getenv("FFB6D_GRID_THREAD_SEARCH")) g_force_thread_search = atoi(e) != 0;
-    if (const char *e = getenv("FFB6D_GRID_QUANTILE")) g_quantile = std::min(31, std::max(0, atoi(e)));
-    g_env_read = true;
+    if (g_env_read.load(std::memory_order_acquire)) return;
+    const Env &e = env();
+    if (e.grid_scale > 0.f) g_cell_scale = e.grid_scale;
+    if (e.grid_scale_k1 > 0.f) g_cell_scale_k1 = e.grid_scale_k1;
+    g_force_thread_search = e.grid_thread_search;
+    g_quantile = e.grid_quantile;
+    g_env_read.store(true, std::memory_order_release);
 }
 
 void knn_grid_tune(float cell_scale, int quantile)
@@ -1020,7 +1023,7 @@ static int launch_search(const float *support, const float *query, int64_t B, in
                 query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
     }
     FFB6D_LAUNCH_OK("grid_search_kernel");
-    const int64_t per_item = std::max<int64_t>(1, 4 * kNumSMs / B);
+    const int64_t per_item = std::max<int64_t>(1, 4 * num_sms() / B);
     if (K <= 32) {
         dim3 ogrid((unsigned)std::min<int64_t>(Q, per_item), (unsigned)B);
         grid_overflow_warp_kernel<IdxT><<<ogrid, 256, 0, st>>>(support, query, (int)S, (int)Q, K, qs.state,

@@ -54,6 +54,12 @@ def knn_search(support_pts, query_pts, k, out_dtype=None, algo=0):
     reference's ``cpp_knn_batch_omp`` (NN/knn_.h:14-16).
     CUDA tensors in -> CUDA tensor out (int32 unless ``out_dtype`` says int64), no
     host round trip.
+
+    Deviations from the reference an integrator should know (DESIGN.md "tie contract"):
+    * rows whose K+1 nearest contain EXACT fp32 distance ties (duplicated points, e.g. the datasets'
+      ``np.pad(..., 'wrap')``, ycb_dataset.py:230) are ordered by ascending (distance, index); the
+      reference's order there is its KD-tree's traversal order.  Distances per row are identical.
+    * ``k`` must be in [1, 64] and points 3-D (the reference accepts any k and dim).
     """
     k = int(k)
     if isinstance(support_pts, np.ndarray) or isinstance(query_pts, np.ndarray):
@@ -253,6 +259,17 @@ def choose_gather(rgb_emb, choose):
     f3 = rgb_emb.reshape(B, Cc, -1) if rgb_emb.dim() == 4 and rgb_emb.is_contiguous() else \
         rgb_emb.flatten(2)
     return _gather_max(f3, choose.reshape(B, -1, 1))
+
+
+def check_indices(idx, S):
+    """Raise :class:`ffb6d_b200._lib.FFB6DError` if any element of the CUDA index tensor ``idx`` lies
+    outside ``[0, S)`` (``ffb6d_check_indices``; blocking).  The gather kernels trust their indices where
+    ``torch.gather`` raises a device assert; set ``FFB6D_CHECK_INDICES=1`` to run this check in front of
+    every gather (debugging aid, synchronises)."""
+    _need_cuda(idx, "idx")
+    idx_c, i64 = _idx_arg(idx, "idx")
+    with torch.cuda.device(idx_c.device):
+        check(lib.ffb6d_check_indices(idx_c.data_ptr(), i64, idx_c.numel(), int(S), _stream(idx_c.device)))
 
 
 # --------------------------------------------------------------------------- neighbour gather

@@ -100,6 +100,7 @@ class FusionPass:
             return outs
         # the 23 gathers are independent of each other too
         main = torch.cuda.current_stream(self.device)
+        capturing = torch.cuda.is_current_stream_capturing()
         order = sorted(range(n), key=lambda i: -(self.gathers[i][2] * self.gathers[i][4]))
         gs = self.gstreams if events is not None else self.streams
         for st in gs:
@@ -111,8 +112,15 @@ class FusionPass:
                 st.wait_event(events[key])
             with torch.cuda.stream(st):
                 outs[i] = self._gather(op, C, self.features[i], inputs[key])
+            if not capturing:
+                # produced on a search stream, read here / produced here, read on the caller's stream:
+                # tell the caching allocator (inside a capture the graph's private pool keeps them alive)
+                inputs[key].record_stream(st)
+                outs[i].record_stream(main)
         for st in (self.streams + self.gstreams) if events is not None else gs:
             main.wait_stream(st)
+        if events is not None:
+            events.pop("_keepalive", None)   # every search has been joined: the grids may go
         return outs
 
     # -- CUDA-graph replay: the pass is ~200 small launches with static shapes ----------

@@ -154,11 +154,17 @@ int ffb6d_knn_host(const float *points, size_t npts, size_t dim,
  * (models/ffb6d.py:309-312).  Pure selection: results are bitwise equal to the
  * reference (NaN propagates like torch.max).
  *   feat [B,C,S] f32 in `layout`, idx [B,Q,K] -> out [B,C,Q] f32 in `layout`.
- * Indices must lie in [0,S); they are not checked (torch.gather would raise).
+ * Indices must lie in [0,S).  The forward kernels do not check them (an offender reads a stale or
+ * foreign element where torch.gather raises a device assert); the backward kernels skip offenders.
+ * Debugging aid: ffb6d_check_indices below, or FFB6D_CHECK_INDICES=1 in the environment, which runs
+ * that check (and synchronises the stream) in front of every gather entry point.
  */
 int ffb6d_gather_max_fwd(const float *feat, const void *idx, int idx_is_i64,
                          int64_t B, int64_t C, int64_t S, int64_t Q, int K,
                          int layout, float *out, ffb6d_stream_t stream);
+/* Validates `count` indices against [0,S): returns FFB6D_ERR_INVALID (with the number of offenders
+ * in ffb6d_last_error) if any lies outside.  Blocking: synchronises `stream`; not capturable. */
+int ffb6d_check_indices(const void *idx, int idx_is_i64, int64_t count, int64_t S, ffb6d_stream_t stream);
 /* Name of the kernel ffb6d_gather_max_fwd launches for a shape (for profiling tools). */
 const char *ffb6d_gather_kernel_name(int64_t B, int64_t C, int64_t S, int64_t Q, int K, int layout);
 /*

@@ -207,8 +207,13 @@ def lfa_cases():
         if isinstance(node, ast.ClassDef) and node.name in ("Dilated_res_block", "Building_block", "Att_pooling"):
             exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
     cases = {}
-    for name, (d_in, d_out, B, N, K, seed) in {"blk_8_16": (8, 16, 2, 96, 16, 0),
-                                               "blk_32_32": (32, 32, 1, 40, 16, 1)}.items():
+    # two toy blocks + the four encoder blocks of FFB6D's RandLA branch at their real widths
+    # (d_in -> 2*d_out = 8->64, 64->128, 128->256, 256->512; common.py:26) and point counts N_i / 4
+    # (a quarter of the real N keeps the fixture small; channel widths are what select the kernels)
+    shapes = {"blk_8_16": (8, 16, 2, 96, 16, 0), "blk_32_32": (32, 32, 1, 40, 16, 1),
+              "ffb6d_ds0": (8, 32, 1, 3072, 16, 2), "ffb6d_ds1": (64, 64, 1, 768, 16, 3),
+              "ffb6d_ds2": (128, 128, 1, 192, 16, 4), "ffb6d_ds3": (256, 256, 1, 48, 16, 5)}
+    for name, (d_in, d_out, B, N, K, seed) in shapes.items():
         torch.manual_seed(seed)
         blk = ns["Dilated_res_block"](d_in, d_out)
         g = torch.Generator().manual_seed(100 + seed)
@@ -235,10 +240,20 @@ def lfa_cases():
     return cases
 
 
+def train_cases():
+    return {}
+
+
 def main():
     if not R.reference_sources_present():
         raise SystemExit("needs /root/reference")
     R.build_ref()
+    if len(sys.argv) > 2 and sys.argv[1] == "--only":      # regenerate one fixture file
+        which = sys.argv[2]
+        fn = {"lfa": lfa_cases, "knn": knn_cases, "gather": gather_cases, "grid": grid_cases, "train": train_cases}[which]
+        np.savez_compressed(os.path.join(OUT, which + "_cases.npz"), **fn())
+        print("rewrote", which + "_cases.npz")
+        return
     np.savez_compressed(os.path.join(OUT, "knn_cases.npz"), **knn_cases())
     np.savez_compressed(os.path.join(OUT, "gather_cases.npz"), **gather_cases())
     np.savez_compressed(os.path.join(OUT, "grid_cases.npz"), **grid_cases())

@@ -12,6 +12,20 @@ import ffb6d_b200 as F
 pytestmark = pytest.mark.gpu
 
 
+def _record(name, err_of_scale, rel, rel32):
+    """Append the measured errors to gpurun_out/mlp_errors.jsonl (DESIGN.md quotes them)."""
+    import json
+    import os
+    from conftest import ROOT
+    try:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "mlp_errors.jsonl"), "a") as fh:
+            fh.write(json.dumps({"layer": name, "max_abs_err_over_scale": err_of_scale, "max_rel_err_above_floor": rel,
+                                 "torch_fp32_rel": rel32}) + "\n")
+    except OSError:
+        pass
+
+
 def reference_layer(x1, x2, conv, bn, relu=True, dtype=torch.float64):
     x = torch.cat((x1, x2), dim=1) if x2 is not None else x1
     y = nn.functional.conv2d(x.to(dtype), conv.weight.to(dtype))
@@ -68,6 +82,15 @@ def test_fusion_mlp_matches_reference_layer(cuda, case):
         torch.backends.cudnn.allow_tf32 = prev
     err32 = (fp32.double() - want).abs().max().item()
     assert err <= max(8 * err32, 2e-6 * max(ref_scale, 1.0)), (err, err32)
+    # element-wise relative error above an absolute floor of 10 % of the output scale (outputs near zero
+    # are sums of K cancelling fp32 products: their error scales with the terms, not with the result);
+    # 1e-5, or what torch's own fp32 path shows on the same elements if that is larger
+    big = want.abs() > 0.1 * max(ref_scale, 1.0)
+    if big.any():
+        rel = ((got.double() - want).abs()[big] / want.abs()[big]).max().item()
+        rel32 = ((fp32.double() - want).abs()[big] / want.abs()[big]).max().item()
+        _record("%d+%d->%d x%d" % (C1, C2, Co, int(np.prod(tail))), err / max(ref_scale, 1.0), rel, rel32)
+        assert rel <= max(1e-5, 4 * rel32), "element-wise relative err %.3e (torch fp32: %.3e)" % (rel, rel32)
     # without ReLU
     got_lin = F.fusion_mlp(x1, x2, conv.weight, scale, shift, relu=False)
     want_lin = reference_layer(x1, x2, conv, bn, relu=False)

@@ -26,12 +26,18 @@ def load_case(path, name):
 
 
 def close(got, want, what):
+    """1e-5 of the output scale for every element AND element-wise relative 1e-4 above an absolute
+    floor of 1e-3 of the scale (a composition of six fp32 GEMM layers: the reference's own CPU/GPU
+    paths differ by this much)."""
     scale = max(np.abs(want).max(), 1.0)
-    err = np.abs(got.astype(np.float64) - want).max()
-    assert err <= 1e-5 * scale, "%s: max abs err %.3e, output scale %.3e" % (what, err, scale)
+    d = np.abs(got.astype(np.float64) - want)
+    assert d.max() <= 1e-5 * scale, "%s: max abs err %.3e, output scale %.3e" % (what, d.max(), scale)
+    big = np.abs(want) > 1e-3 * scale
+    rel = (d[big] / np.abs(want[big])).max() if big.any() else 0.0
+    assert rel <= 1e-4, "%s: max element-wise relative err %.3e" % (what, rel)
 
 
-@pytest.mark.parametrize("name", ["blk_8_16", "blk_32_32"])
+@pytest.mark.parametrize("name", ["blk_8_16", "blk_32_32", "ffb6d_ds0", "ffb6d_ds1", "ffb6d_ds2", "ffb6d_ds3"])
 def test_dilated_res_block_matches_reference(cuda, name):
     import os
     from conftest import GOLDEN
