@@ -5,13 +5,11 @@
 // fp32 distance, ordered by (distance, index) -- is produced by binning the support into a
 // uniform grid and scanning only the cells around each query:
 //
-//   A. prepare  : per batch item min/max of the support (chunked over CTAs; the last CTA to
-//                 finish reduces the partials), an ESTIMATE of the K-th neighbour distance from
-//                 32 sample points scanned against a strided subsample, and from it the cell
-//                 edge h and grid dims; the item's cell counters are zeroed
-//   B. count    : one atomic per point into its cell's counter (+ a per-4096-cell tile total)
-//   C. scan     : exclusive prefix sum of the counters (cell -> first slot), one CTA per tile
-//   D. scatter  : points (x,y,z,index) written cell-contiguous as float4
+//   A-D. build  : ONE kernel, a cluster of 8 CTAs per batch item (grid_build_kernel): bounding box,
+//                 an ESTIMATE of the K-th neighbour distance from 32 sample points scanned against
+//                 a strided subsample -> cell edge h and grid dims; counting sort of the points
+//                 into cells (one atomic per point, prefix sum of the cell counters, points
+//                 (x,y,z,index) written cell-contiguous as float4)
 //   E. search   : one thread per query scans the (2r+1)^3 block of cells around it, r = 1..RMAX
 //                 (each ring adds only its shell of cells), keeping a sorted top-K in registers; a row of cells along x is one contiguous
 //                 range of the sorted array, read four points at a time.  The search stops as
@@ -39,10 +37,12 @@
 namespace ffb6d {
 
 constexpr int RMAX = 4;                 // widest block: 9x9x9 cells
-constexpr int PREP_THREADS = 1024;
-constexpr int MAX_CHUNKS = 64;          // partial bboxes per batch item
-constexpr int TILE_CELLS = 4096;        // cells per scan tile
-constexpr int N_SAMPLES = 32;           // one per warp of the prepare CTA
+constexpr int N_SAMPLES = 32;           // sample points of the K-th-distance estimate
+constexpr int BUILD_CTAS = 8;           // thread-block cluster that builds one batch item's grid
+constexpr int BUILD_THREADS = 512;
+constexpr int BUILD_WARPS = BUILD_THREADS / 32;
+constexpr int BUILD_GT = BUILD_CTAS * BUILD_THREADS;   // threads per batch item
+static_assert(N_SAMPLES == BUILD_CTAS * 4 && BUILD_WARPS == 16, "4 samples per CTA, 4 warps per sample");
 
 struct __align__(16) GridParams {
     float lo[3];
@@ -68,12 +68,10 @@ struct __align__(16) QueryState {
 // number of query calls (on any stream ordered after the build) can share it.
 struct GridStore {
     GridParams *params;   // [B]
-    int *ticket;          // [B]   CTAs of the prepare kernel that have finished
-    float *partial;       // [B][MAX_CHUNKS][6]
-    int *tile_sum;        // [B][ntiles]
-    int *cursor;          // [B][maxc]  counts -> exclusive starts -> ends
-    float4 *sorted;       // [B][S]
-    size_t maxc, ntiles;
+    int *cursor;          // [B][maxc]  counts -> inclusive prefix = END offset of every cell
+    int *rank;            // [B][S]     arrival rank of a point inside its cell (build scratch)
+    float4 *sorted;       // [B][S]     (x, y, z, original index), cell-contiguous
+    size_t maxc;
     size_t bytes;
 };
 
@@ -89,14 +87,13 @@ static size_t max_cells_for(int64_t S)
     size_t m = (size_t)S * 8;   // 32 cells per point measured slower (more empty rows to look up)
     if (m < 4096) m = 4096;
     if (m > ((size_t)1 << 22)) m = (size_t)1 << 22;
-    return (m + TILE_CELLS - 1) / TILE_CELLS * TILE_CELLS;   // whole scan tiles, 16-byte aligned rows
+    return (m + 4095) / 4096 * 4096;   // 16-byte aligned rows
 }
 
 static GridStore carve_grid(void *base, int64_t B, int64_t S)
 {
     GridStore w;
     w.maxc = max_cells_for(S);
-    w.ntiles = (w.maxc + TILE_CELLS - 1) / TILE_CELLS;
     size_t off = 0;
     char *p = (char *)base;
     auto take = [&](size_t bytes) {
@@ -105,10 +102,8 @@ static GridStore carve_grid(void *base, int64_t B, int64_t S)
         return r;
     };
     w.params = (GridParams *)take((size_t)B * sizeof(GridParams));
-    w.ticket = (int *)take((size_t)B * sizeof(int));
-    w.partial = (float *)take((size_t)B * MAX_CHUNKS * 6 * sizeof(float));
-    w.tile_sum = (int *)take((size_t)B * w.ntiles * sizeof(int));
     w.cursor = (int *)take((size_t)B * w.maxc * sizeof(int));
+    w.rank = (int *)take((size_t)B * (size_t)S * sizeof(int));
     w.sorted = (float4 *)take((size_t)B * (size_t)S * sizeof(float4));
     w.bytes = off;
     return w;
@@ -130,7 +125,7 @@ static QueryScratch carve_query(void *base, int64_t B, int64_t Q)
 size_t knn_grid_store_bytes(int64_t B, int64_t S) { return carve_grid(nullptr, B, S).bytes; }
 size_t knn_grid_query_bytes(int64_t B, int64_t Q) { return carve_query(nullptr, B, Q).bytes; }
 
-// The grid pays off once the all-pairs scan is big enough to dwarf its seven small launches.
+// The grid pays off once the all-pairs scan is big enough to dwarf its launches.
 static bool grid_worthwhile(int64_t B, int64_t S, int64_t Q, int K)
 {
     (void)B;
@@ -150,120 +145,125 @@ __device__ __forceinline__ int cell_of(float p, float lo, float inv_h, int n)
     return min(max(c, 0), n - 1);
 }
 
-// ------------------------------------------------------------------ A. prepare
-__global__ void __launch_bounds__(PREP_THREADS)
-grid_prepare_kernel(const float *__restrict__ support, int S, int K, int chunk, int nchunks,
-                    int maxc, int ntiles, float cell_scale, int quantile, GridParams *__restrict__ params,
-                    int *__restrict__ ticket, float *__restrict__ partial)
+// ------------------------------------------------------------------ A-D. grid build: ONE kernel
+// A thread-block cluster of 8 CTAs (4096 threads) builds the grid of one batch item; the phases
+// are separated by hardware cluster barriers and exchange their small results through distributed
+// shared memory, so the whole build is a single launch (it was five):
+//   1. partial bounding box per CTA; the K-th-neighbour-distance ESTIMATE: 32 sample points, four
+//      per CTA, four warps per sample, each warp scanning a quarter of a strided subsample of the
+//      support (k' points of the subsample stand for k'*stride >= K points of the cloud)
+//   2. rank 0 gathers the 8 boxes and 32 estimates over DSMEM, picks the quantile, derives the
+//      cell edge h and the grid dims, publishes the parameters
+//   3. the cell counters that exist are zeroed
+//   4. count: one atomic per point; the value it returns is the point's arrival rank inside its
+//      cell, kept for step 6 (no second round of atomics); per-CTA totals of the 8 scan slices
+//   5. inclusive prefix sum of the counters (cell -> END offset): every CTA scans one slice, its
+//      warps own contiguous runs (coalesced 512-byte steps, shuffles only, no CTA barrier inside)
+//   6. scatter: point -> sorted[end(cell-1) + rank] as float4 (x, y, z, original index)
+// The order of the points inside a cell depends on the atomics' arrival order; search results do
+// not (candidates are ranked by the total order (distance, index)).
+__global__ void __cluster_dims__(BUILD_CTAS, 1, 1) __launch_bounds__(BUILD_THREADS)
+grid_build_kernel(const float *__restrict__ support, int S, int K, int maxc, float cell_scale, int quantile,
+                  GridParams *__restrict__ params, int *__restrict__ cursor_all, int *__restrict__ rank_all,
+                  float4 *__restrict__ sorted_all)
 {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int crank = (int)cluster.block_rank();
     const int b = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int gtid = crank * BUILD_THREADS + tid;
     const float *sup = support + (size_t)b * S * 3;
+    int *cur = cursor_all + (size_t)b * maxc;
+    int *rnk = rank_all + (size_t)b * S;
+    float4 *sorted = sorted_all + (size_t)b * S;
     const float INF = __int_as_float(0x7f800000);
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    __shared__ float red[6][32];
-    __shared__ float est[N_SAMPLES];
-    __shared__ float est_pick;
-    __shared__ int flag;
 
-    // ---- partial bounding box of this CTA's chunk
-    float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
-    const int s_begin = blockIdx.x * chunk, s_end = min(S, s_begin + chunk);
-    for (int s = s_begin + threadIdx.x; s < s_end; s += PREP_THREADS) {
+    __shared__ float s_red[6][BUILD_WARPS];
+    __shared__ float s_box[6];              // this CTA's partial bounding box
+    __shared__ float s_cand[4][4][4];       // [sample of this CTA][warp of the sample][k']
+    __shared__ float s_est[4];              // this CTA's four estimates
+    __shared__ float s_all[N_SAMPLES];      // rank 0: all estimates
+    __shared__ float s_pick;
+    __shared__ GridParams s_P;              // rank 0 publishes, everybody copies
+    __shared__ int s_tot[BUILD_CTAS];       // points this CTA counted into each scan slice
+    __shared__ int s_wsum[BUILD_WARPS];
+    __shared__ int s_base;
+
+    // ---- 1a. partial bounding box
+    {
+        float mn[3] = {INF, INF, INF}, mx[3] = {-INF, -INF, -INF};
+        for (int s = gtid; s < S; s += BUILD_GT) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                const float v = __ldg(sup + (size_t)s * 3 + a);
+                mn[a] = fminf(mn[a], v);
+                mx[a] = fmaxf(mx[a], v);
+            }
+        }
 #pragma unroll
         for (int a = 0; a < 3; ++a) {
-            const float v = __ldg(sup + (size_t)s * 3 + a);
-            mn[a] = fminf(mn[a], v);
-            mx[a] = fmaxf(mx[a], v);
-        }
-    }
-#pragma unroll
-    for (int a = 0; a < 3; ++a) {
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
-            mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
-        }
-        if (lane == 0) {
-            red[a][wid] = mn[a];
-            red[3 + a][wid] = mx[a];
-        }
-    }
-    __syncthreads();
-    if (wid == 0) {
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            float u = red[a][lane], v = red[3 + a][lane];
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) {
-                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, o));
-                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                mn[a] = fminf(mn[a], __shfl_xor_sync(0xffffffffu, mn[a], o));
+                mx[a] = fmaxf(mx[a], __shfl_xor_sync(0xffffffffu, mx[a], o));
             }
             if (lane == 0) {
-                partial[((size_t)b * MAX_CHUNKS + blockIdx.x) * 6 + a] = u;
-                partial[((size_t)b * MAX_CHUNKS + blockIdx.x) * 6 + 3 + a] = v;
+                s_red[a][wid] = mn[a];
+                s_red[3 + a][wid] = mx[a];
+            }
+        }
+        if (tid < BUILD_CTAS) s_tot[tid] = 0;
+        __syncthreads();
+        if (wid == 0) {
+#pragma unroll
+            for (int a = 0; a < 3; ++a) {
+                float u = lane < BUILD_WARPS ? s_red[a][lane] : INF, v = lane < BUILD_WARPS ? s_red[3 + a][lane] : -INF;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    u = fminf(u, __shfl_xor_sync(0xffffffffu, u, o));
+                    v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+                }
+                if (lane == 0) {
+                    s_box[a] = u;
+                    s_box[3 + a] = v;
+                }
             }
         }
     }
-    // ---- the last CTA of this batch item to get here finishes the job
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) flag = (atomicAdd(ticket + b, 1) == nchunks - 1);
-    __syncthreads();
-    if (!flag) return;
-    __threadfence();
-
-    if (wid == 0) {   // full bbox from the partials
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            float u = INF, v = -INF;
-            for (int c = lane; c < nchunks; c += 32) {
-                u = fminf(u, __ldcg(partial + ((size_t)b * MAX_CHUNKS + c) * 6 + a));
-                v = fmaxf(v, __ldcg(partial + ((size_t)b * MAX_CHUNKS + c) * 6 + 3 + a));
-            }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) {
-                u = fminf(u, __shfl_xor_sync(0xffffffffu, u, o));
-                v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-            }
-            if (lane == 0) {
-                red[a][0] = u;
-                red[3 + a][0] = v;
-            }
-        }
-    }
-
-    // ---- estimate of the K-th neighbour distance: warp w scans a strided subsample of the
-    // support around sample point w and extracts the kk-th smallest distance, where kk points of
-    // the subsample stand for kk*stride >= K points of the full cloud (dimension-free).
+    // ---- 1b. estimate of the K-th neighbour distance (does not need the box)
     {
         const int stride = max((S + 4095) / 4096, (K + 3) / 4);
         const int kk = max(1, (K + stride - 1) / stride);          // <= 4
-        const int me = (int)((((long long)wid * S) / N_SAMPLES + S / (2 * N_SAMPLES)) % max(S, 1));
-        float r = 0.f;
+        const int smp = crank * 4 + (wid >> 2), w4 = wid & 3;
+        const int me = (int)((((long long)smp * S) / N_SAMPLES + S / (2 * N_SAMPLES)) % max(S, 1));
+        float out[4] = {INF, INF, INF, INF};
         if (S > 1) {
             const float qx = __ldg(sup + (size_t)me * 3), qy = __ldg(sup + (size_t)me * 3 + 1),
                         qz = __ldg(sup + (size_t)me * 3 + 2);
             TopK<4> t4;
             t4.init();
-            for (int s0 = lane * stride; s0 < S; s0 += 4 * 32 * stride) {   // 12 loads in flight
+            const int nsub = (S + stride - 1) / stride;              // subsample = points 0, stride, 2*stride, ...
+            for (int i0 = w4 * 32 + lane; i0 < nsub; i0 += 4 * 128) {   // 12 loads in flight
                 float px[4], py[4], pz[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int s = min(s0 + u * 32 * stride, S - 1);
+                    const int s = min((i0 + u * 128) * stride, S - 1);
                     px[u] = __ldg(sup + (size_t)s * 3);
                     py[u] = __ldg(sup + (size_t)s * 3 + 1);
                     pz[u] = __ldg(sup + (size_t)s * 3 + 2);
                 }
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                    const int s = s0 + u * 32 * stride;
+                    const int i = i0 + u * 128, s = i * stride;
                     const float d = ref_sqdist(qx, qy, qz, px[u], py[u], pz[u]);
-                    if (s < S && s != me && d < t4.worst()) t4.push_ordered(d, s);
+                    if (i < nsub && s != me && d < t4.worst()) t4.push_ordered(d, s);
                 }
             }
-            float m = INF;
-            for (int round = 0; round < kk; ++round) {   // pop the warp-wide minimum kk times
-                m = t4.d[0];
+#pragma unroll
+            for (int round = 0; round < 4; ++round) {   // pop this warp's minimum kk (<= 4) times
+                if (round >= kk) break;
+                float m = t4.d[0];
 #pragma unroll
                 for (int o = 16; o > 0; o >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, o));
                 const unsigned who = __ballot_sync(0xffffffffu, t4.d[0] == m);
@@ -273,184 +273,214 @@ grid_prepare_kernel(const float *__restrict__ support, int S, int K, int chunk, 
                     t4.d[2] = t4.d[3];
                     t4.d[3] = INF;
                 }
+                out[round] = m;
+            }
+        }
+        if (lane == 0) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) s_cand[wid >> 2][w4][j] = out[j];
+        }
+        __syncthreads();
+        if (wid < 4) {   // the kk-th smallest of the sample's 16 candidates
+            const float mine = lane < 16 ? s_cand[wid][lane >> 2][lane & 3] : INF;
+            int rank = 0;
+            for (int j = 0; j < 16; ++j) {
+                const float o = __shfl_sync(0xffffffffu, mine, j);
+                rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
             }
             // kk*stride-th neighbour measured; scale to the K-th assuming a 2-D sheet
-            r = sqrtf(m) * sqrtf((float)K / (float)(kk * stride));
-        }
-        if (lane == 0) est[wid] = (r == r && r < INF) ? r : 0.f;
-    }
-    __syncthreads();
-    // the `quantile`-th smallest of the 32 estimates (hole pixels give zeros: they rank first)
-    if (wid == 0) {
-        const float mine = est[lane];
-        int rank = 0;
-        for (int j = 0; j < N_SAMPLES; ++j) {
-            const float o = est[j];
-            rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
-        }
-        if (rank == quantile) est_pick = mine;
-    }
-    __syncthreads();
-
-    if (threadIdx.x == 0) {
-        for (int a = 0; a < 3; ++a) {
-            mn[a] = red[a][0];
-            mx[a] = red[3 + a][0];
-        }
-        const float r_est = est_pick;
-
-        GridParams P;
-        float L[3], scale = 0.f;
-        bool finite = true;
-        for (int a = 0; a < 3; ++a) {
-            L[a] = mx[a] - mn[a];
-            finite = finite && isfinite(L[a]) && isfinite(mn[a]);
-            scale = fmaxf(scale, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
-            P.lo[a] = mn[a];
-            P.hi[a] = mx[a];
-        }
-        const float l1 = fmaxf(L[0], fmaxf(L[1], L[2]));
-        const float l3 = fminf(L[0], fminf(L[1], L[2]));
-        const float l2 = L[0] + L[1] + L[2] - l1 - l3;
-        float h = cell_scale * r_est;
-        if (!(h > 0.f)) h = sqrtf((float)K * l1 * l2 / (float)max(S, 1));   // geometric fallback
-        if (!(h > 0.f)) h = l1 * (float)K / (float)max(S, 1);               // points on a line
-        int n[3] = {1, 1, 1};
-        if (finite && h > 0.f && l1 > 0.f) {
-            for (int it = 0; it < 200; ++it) {
-                double prod = 1.0;
-                for (int a = 0; a < 3; ++a) {
-                    const float f = floorf(L[a] / h);
-                    n[a] = (f >= 4.0e6f) ? 4000000 : (int)f + 1;
-                    prod *= (double)n[a];
-                }
-                if (prod <= (double)maxc) break;
-                h *= 1.2f;
-                if (it == 199) n[0] = n[1] = n[2] = 1;
+            if (lane < 16 && rank == kk - 1) {
+                const float r = (S > 1) ? sqrtf(mine) * sqrtf((float)K / (float)(kk * stride)) : 0.f;
+                s_est[wid] = (r == r && r < INF) ? r : 0.f;
             }
         }
-        const bool single = (n[0] == 1 && n[1] == 1 && n[2] == 1);
-        P.h = single ? INF : h;
-        P.inv_h = single ? 0.f : 1.0f / h;
-        P.slack = 1e-5f * (scale + l1) + 1e-30f;
-        P.n[0] = n[0];
-        P.n[1] = n[1];
-        P.n[2] = n[2];
-        P.ncells = n[0] * n[1] * n[2];
-        for (int a = 0; a < 3; ++a) P.pad[a] = 0;
-        params[b] = P;
-        ticket[b] = 0;   // ready for the next build on this storage
     }
-}
-
-// ------------------------------------------------------------------ A'. zero the cell counters that exist
-__global__ void __launch_bounds__(256)
-grid_zero_kernel(const GridParams *__restrict__ params, int *__restrict__ cursor, size_t cursor_stride,
-                 int *__restrict__ tile_sum, int ntiles)
-{
-    const int b = blockIdx.y, tile = blockIdx.x;
-    const int n = params[b].ncells;
-    if (tile * TILE_CELLS >= n) return;
-    int4 *c = reinterpret_cast<int4 *>(cursor + (size_t)b * cursor_stride + (size_t)tile * TILE_CELLS);
-    // whole tiles are zeroed (the budget is a multiple of the tile): simpler and still tiny
-    for (int i = threadIdx.x; i < TILE_CELLS / 4; i += blockDim.x) c[i] = make_int4(0, 0, 0, 0);
-    if (threadIdx.x == 0) tile_sum[(size_t)b * ntiles + tile] = 0;
-}
-
-// ------------------------------------------------------------------ B. count
-__global__ void __launch_bounds__(256)
-grid_count_kernel(const float *__restrict__ support, int S, const GridParams *__restrict__ params,
-                  int *__restrict__ cursor, size_t cursor_stride, int *__restrict__ tile_sum,
-                  int ntiles)
-{
-    __shared__ int tiles[1024];   // per-CTA tile totals (ntiles <= 4M / 4096)
-    const int b = blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    const GridParams &P = params[b];
-    const int used = (P.ncells + TILE_CELLS - 1) / TILE_CELLS;
-    for (int i = threadIdx.x; i < used; i += blockDim.x) tiles[i] = 0;
-    __syncthreads();
-    if (s < S) {
-        const float *p = support + ((size_t)b * S + s) * 3;
-        const int cx = cell_of(__ldg(p), P.lo[0], P.inv_h, P.n[0]);
-        const int cy = cell_of(__ldg(p + 1), P.lo[1], P.inv_h, P.n[1]);
-        const int cz = cell_of(__ldg(p + 2), P.lo[2], P.inv_h, P.n[2]);
-        const int cell = (cz * P.n[1] + cy) * P.n[0] + cx;
-        atomicAdd(cursor + (size_t)b * cursor_stride + cell, 1);
-        atomicAdd(&tiles[cell / TILE_CELLS], 1);
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < used; i += blockDim.x)
-        if (tiles[i]) atomicAdd(tile_sum + (size_t)b * ntiles + i, tiles[i]);
-}
-
-// ------------------------------------------------------------------ C. exclusive scan, one CTA per tile
-__global__ void __launch_bounds__(1024)
-grid_scan_kernel(const GridParams *__restrict__ params, int *__restrict__ cursor,
-                 size_t cursor_stride, const int *__restrict__ tile_sum, int ntiles)
-{
-    const int b = blockIdx.y, tile = blockIdx.x;
-    const int n = params[b].ncells;
-    if (tile * TILE_CELLS >= n) return;
-    int *c = cursor + (size_t)b * cursor_stride + (size_t)tile * TILE_CELLS;
-    const int cnt = min(TILE_CELLS, n - tile * TILE_CELLS);
-    __shared__ int warp_tot[32];
-    __shared__ int base_s;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    if (wid == 0) {   // total of all earlier tiles
-        int acc = 0;
-        for (int t = lane; t < tile; t += 32) acc += tile_sum[(size_t)b * ntiles + t];
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) base_s = acc;
-    }
-    const int i = threadIdx.x * 4;
-    int v[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) v[j] = (i + j < cnt) ? c[i + j] : 0;
-    const int t = v[0] + v[1] + v[2] + v[3];
-    int incl = t;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const int u = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += u;
-    }
-    if (lane == 31) warp_tot[wid] = incl;
-    __syncthreads();
-    if (wid == 0) {
-        int w = warp_tot[lane];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int u = __shfl_up_sync(0xffffffffu, w, o);
-            if (lane >= o) w += u;
+    cluster.sync();
+    // ---- 2. rank 0: full box, quantile of the estimates, grid parameters
+    if (crank == 0) {
+        if (wid == 0) {
+            s_all[lane] = cluster.map_shared_rank(s_est, lane >> 2)[lane & 3];
+            if (lane < 6) {
+                float v = (lane < 3) ? INF : -INF;
+                for (int c = 0; c < BUILD_CTAS; ++c) {
+                    const float o = cluster.map_shared_rank(s_box, c)[lane];
+                    v = (lane < 3) ? fminf(v, o) : fmaxf(v, o);
+                }
+                s_red[lane][0] = v;
+            }
+            __syncwarp();
+            // the `quantile`-th smallest of the 32 estimates (hole pixels give zeros: they rank first)
+            const float mine = s_all[lane];
+            int rank = 0;
+            for (int j = 0; j < N_SAMPLES; ++j) {
+                const float o = s_all[j];
+                rank += (o < mine || (o == mine && j < lane)) ? 1 : 0;
+            }
+            if (rank == quantile) s_pick = mine;
+            __syncwarp();
+            if (lane == 0) {
+                float mn[3], mx[3];
+                for (int a = 0; a < 3; ++a) {
+                    mn[a] = s_red[a][0];
+                    mx[a] = s_red[3 + a][0];
+                }
+                const float r_est = s_pick;
+                GridParams P;
+                float L[3], scale = 0.f;
+                bool finite = true;
+                for (int a = 0; a < 3; ++a) {
+                    L[a] = mx[a] - mn[a];
+                    finite = finite && isfinite(L[a]) && isfinite(mn[a]);
+                    scale = fmaxf(scale, fmaxf(fabsf(mn[a]), fabsf(mx[a])));
+                    P.lo[a] = mn[a];
+                    P.hi[a] = mx[a];
+                }
+                const float l1 = fmaxf(L[0], fmaxf(L[1], L[2]));
+                const float l3 = fminf(L[0], fminf(L[1], L[2]));
+                const float l2 = L[0] + L[1] + L[2] - l1 - l3;
+                float h = cell_scale * r_est;
+                if (!(h > 0.f)) h = sqrtf((float)K * l1 * l2 / (float)max(S, 1));   // geometric fallback
+                if (!(h > 0.f)) h = l1 * (float)K / (float)max(S, 1);               // points on a line
+                int n[3] = {1, 1, 1};
+                if (finite && h > 0.f && l1 > 0.f) {
+                    for (int it = 0; it < 200; ++it) {
+                        double prod = 1.0;
+                        for (int a = 0; a < 3; ++a) {
+                            const float f = floorf(L[a] / h);
+                            n[a] = (f >= 4.0e6f) ? 4000000 : (int)f + 1;
+                            prod *= (double)n[a];
+                        }
+                        if (prod <= (double)maxc) break;
+                        h *= 1.2f;
+                        if (it == 199) n[0] = n[1] = n[2] = 1;
+                    }
+                }
+                const bool single = (n[0] == 1 && n[1] == 1 && n[2] == 1);
+                P.h = single ? INF : h;
+                P.inv_h = single ? 0.f : 1.0f / h;
+                P.slack = 1e-5f * (scale + l1) + 1e-30f;
+                P.n[0] = n[0];
+                P.n[1] = n[1];
+                P.n[2] = n[2];
+                P.ncells = n[0] * n[1] * n[2];
+                for (int a = 0; a < 3; ++a) P.pad[a] = 0;
+                s_P = P;
+                params[b] = P;
+            }
         }
-        warp_tot[lane] = w;
     }
+    cluster.sync();
+    if (crank != 0 && tid < 16)   // one 64-byte DSMEM read per CTA
+        reinterpret_cast<float *>(&s_P)[tid] = reinterpret_cast<const float *>(cluster.map_shared_rank(&s_P, 0))[tid];
     __syncthreads();
-    int run = base_s + (wid ? warp_tot[wid - 1] : 0) + incl - t;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        if (i + j < cnt) c[i + j] = run;
-        run += v[j];
+    const GridParams P = s_P;
+    const int ncells = P.ncells;
+    // scan slices: 8 equal runs of cells, a multiple of 128 cells each (whole 512-byte warp steps)
+    const int slice = ((ncells + BUILD_CTAS * 128 - 1) / (BUILD_CTAS * 128)) * 128;
+    // ---- 3. zero the counters that exist
+    {
+        int4 *c4 = reinterpret_cast<int4 *>(cur);
+        const int n4 = min((ncells + 3) / 4, maxc / 4);
+        for (int i = gtid; i < n4; i += BUILD_GT) c4[i] = make_int4(0, 0, 0, 0);
     }
-}
-
-// ------------------------------------------------------------------ D. scatter
-__global__ void __launch_bounds__(256)
-grid_scatter_kernel(const float *__restrict__ support, int S, const GridParams *__restrict__ params,
-                    int *__restrict__ cursor, size_t cursor_stride, float4 *__restrict__ sorted)
-{
-    const int b = blockIdx.y;
-    const int s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= S) return;
-    const GridParams &P = params[b];
-    const float *p = support + ((size_t)b * S + s) * 3;
-    const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
-    const int cx = cell_of(x, P.lo[0], P.inv_h, P.n[0]);
-    const int cy = cell_of(y, P.lo[1], P.inv_h, P.n[1]);
-    const int cz = cell_of(z, P.lo[2], P.inv_h, P.n[2]);
-    const int pos = atomicAdd(cursor + (size_t)b * cursor_stride + ((size_t)cz * P.n[1] + cy) * P.n[0] + cx, 1);
-    sorted[(size_t)b * S + pos] = make_float4(x, y, z, __int_as_float(s));
+    cluster.sync();
+    // ---- 4. count (the returned value is the point's rank inside its cell)
+    {
+        int acc = 0;   // lane j < 8: points this warp put into slice j
+        const int iters = (S + BUILD_GT - 1) / BUILD_GT;
+        for (int it = 0; it < iters; ++it) {
+            const int s = it * BUILD_GT + gtid;
+            int sl = -1;
+            if (s < S) {
+                const float *p = sup + (size_t)s * 3;
+                const int cx = cell_of(__ldg(p), P.lo[0], P.inv_h, P.n[0]);
+                const int cy = cell_of(__ldg(p + 1), P.lo[1], P.inv_h, P.n[1]);
+                const int cz = cell_of(__ldg(p + 2), P.lo[2], P.inv_h, P.n[2]);
+                const int cell = (cz * P.n[1] + cy) * P.n[0] + cx;
+                rnk[s] = atomicAdd(cur + cell, 1);
+                sl = cell / slice;
+            }
+#pragma unroll
+            for (int j = 0; j < BUILD_CTAS; ++j) {
+                const int v = __popc(__ballot_sync(0xffffffffu, sl == j));
+                if (lane == j) acc += v;
+            }
+        }
+        if (lane < BUILD_CTAS && acc) atomicAdd(&s_tot[lane], acc);
+    }
+    cluster.sync();
+    // ---- 5. inclusive prefix sum of slice `crank`
+    {
+        if (wid == 0) {   // points in the slices before mine, summed over the 8 CTAs' tallies
+            int t = 0;
+            if (lane < BUILD_CTAS)
+                for (int c = 0; c < BUILD_CTAS; ++c) t += cluster.map_shared_rank(s_tot, c)[lane];
+            int before = (lane < crank) ? t : 0;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+            if (lane == 0) s_base = before;
+        }
+        const int lo = crank * slice, hi = min(ncells, lo + slice);
+        // warp w owns the contiguous run [wlo, whi) of the slice, a multiple of 128 cells long
+        const int run = ((slice / 128 + BUILD_WARPS - 1) / BUILD_WARPS) * 128;
+        const int wlo = min(hi, lo + wid * run), whi = min(hi, wlo + run);
+        int tot = 0;
+        for (int i = wlo + 4 * lane; i < whi; i += 128) {   // pass 1: total of the run (whi may cut a lane's int4)
+            const int4 v = *reinterpret_cast<const int4 *>(cur + i);
+            tot += v.x + (i + 1 < whi ? v.y : 0) + (i + 2 < whi ? v.z : 0) + (i + 3 < whi ? v.w : 0);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+        if (lane == 0) s_wsum[wid] = tot;
+        __syncthreads();
+        int carry = s_base;
+        for (int w = 0; w < wid; ++w) carry += s_wsum[w];
+        for (int i0 = wlo; i0 < whi; i0 += 128) {           // pass 2: scan, coalesced 512-byte steps
+            const int i = i0 + 4 * lane;
+            int4 v = make_int4(0, 0, 0, 0);
+            if (i < whi) {
+                v = *reinterpret_cast<const int4 *>(cur + i);
+                if (i + 1 >= whi) v.y = 0;
+                if (i + 2 >= whi) v.z = 0;
+                if (i + 3 >= whi) v.w = 0;
+            }
+            const int t = v.x + v.y + v.z + v.w;
+            int incl = t;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(0xffffffffu, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int start = carry + incl - t;
+            if (i < whi) {
+                int4 e;
+                e.x = start + v.x;
+                e.y = e.x + v.y;
+                e.z = e.y + v.z;
+                e.w = e.z + v.w;
+                if (i + 3 < whi) {
+                    *reinterpret_cast<int4 *>(cur + i) = e;
+                } else {
+                    cur[i] = e.x;
+                    if (i + 1 < whi) cur[i + 1] = e.y;
+                    if (i + 2 < whi) cur[i + 2] = e.z;
+                }
+            }
+            carry += __shfl_sync(0xffffffffu, incl, 31);
+        }
+    }
+    cluster.sync();
+    // ---- 6. scatter
+    for (int s = gtid; s < S; s += BUILD_GT) {
+        const float *p = sup + (size_t)s * 3;
+        const float x = __ldg(p), y = __ldg(p + 1), z = __ldg(p + 2);
+        const int cx = cell_of(x, P.lo[0], P.inv_h, P.n[0]);
+        const int cy = cell_of(y, P.lo[1], P.inv_h, P.n[1]);
+        const int cz = cell_of(z, P.lo[2], P.inv_h, P.n[2]);
+        const int cell = (cz * P.n[1] + cy) * P.n[0] + cx;
+        const int pos = (cell > 0 ? cur[cell - 1] : 0) + rnk[s];
+        sorted[pos] = make_float4(x, y, z, __int_as_float(s));
+    }
     // after this kernel cursor[c] is the END of cell c; its start is cursor[c-1] (0 for c == 0)
 }
 
@@ -839,6 +869,220 @@ grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
     }
 }
 
+// ------------------------------------------------------------------ E''. search, HALF a warp per query (K <= 16)
+// Same algorithm as grid_search_warp_kernel with the sorted list spread over the 16 lanes of a
+// half-warp, so one warp answers two neighbouring queries at once: the control flow (segment set-up,
+// prefix sums, binary searches, the ring logic) is issued once for both -- the warp-per-query kernel
+// spends ~750 warp instructions per query, nine tenths of it such bookkeeping (ncu source page), so
+// sharing it nearly halves the cost per query.  Everything that differs between the two queries is
+// carried per lane group (ring, scanned block, done flag) and the loops run while EITHER group has
+// work; a group that is finished keeps executing with empty segments.
+template <int W>
+__device__ __forceinline__ void group_minmax(key_t64 &k, int j, bool keep_min)
+{
+    const key_t64 o = __shfl_xor_sync(0xffffffffu, k, j, W);
+    if ((o < k) == keep_min) k = o;
+}
+
+template <int W>
+__device__ __forceinline__ void group_sort(key_t64 &k, int sub)   // ascending bitonic sort inside a group of W lanes
+{
+#pragma unroll
+    for (int kk = 2; kk <= W; kk <<= 1) {
+#pragma unroll
+        for (int j = kk >> 1; j > 0; j >>= 1) {
+            const bool up = (sub & kk) == 0;
+            group_minmax<W>(k, j, ((sub & j) == 0) == up);
+        }
+    }
+}
+
+template <typename IdxT, bool SELF, int W>
+__global__ void __launch_bounds__(256, 4)
+grid_search_group_kernel(const float *__restrict__ query, int S, int Q, int K,
+                         const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
+                         size_t cursor_stride, const float4 *__restrict__ sorted_all,
+                         IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
+{
+    constexpr int G = 32 / W;                       // queries per warp
+    const unsigned FULL = 0xffffffffu;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, sub = lane & (W - 1), grp = lane / W;
+    const int t = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G + grp;
+    if ((blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * G >= Q) return;   // warp-uniform
+    const bool valid = t < Q;                       // the last warp may hold fewer than G queries
+    const int tq = valid ? t : Q - 1;
+    const GridParams Ps = params_all[b];
+    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
+    const float4 *sorted = sorted_all + (size_t)b * S;
+    float qx, qy, qz;
+    int q;
+    if (SELF) {
+        const float4 me = __ldg(sorted + tq);
+        qx = me.x;
+        qy = me.y;
+        qz = me.z;
+        q = __float_as_int(me.w);
+    } else {
+        const float *qp = query + ((size_t)b * Q + tq) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+        q = tq;
+    }
+    const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
+    const float h = Ps.h, slack = Ps.slack;
+    const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
+    const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
+    const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
+    const float INF = __int_as_float(0x7f800000);
+    const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
+                            fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
+    auto margin = [&](int r) {   // distance to the nearest face of block r that has cells behind it
+        float m = INF;
+        if (cx - r > 0) m = fminf(m, qx - (Ps.lo[0] + (float)(cx - r) * h));
+        if (cx + r < nx - 1) m = fminf(m, (Ps.lo[0] + (float)(cx + r + 1) * h) - qx);
+        if (cy - r > 0) m = fminf(m, qy - (Ps.lo[1] + (float)(cy - r) * h));
+        if (cy + r < ny - 1) m = fminf(m, (Ps.lo[1] + (float)(cy + r + 1) * h) - qy);
+        if (cz - r > 0) m = fminf(m, qz - (Ps.lo[2] + (float)(cz - r) * h));
+        if (cz + r < nz - 1) m = fminf(m, (Ps.lo[2] + (float)(cz + r + 1) * h) - qz);
+        return m;
+    };
+
+    key_t64 mine = KEY_EMPTY;        // lane sub of a group: its sub-th best so far
+    bool done = false;               // group-uniform
+    int r = (out > (float)RMAX * h) ? RMAX + 1 : 1;
+    bool active = valid && r <= RMAX;   // group-uniform: this group still scans rings
+    int e_prev = 0, px0 = 0, px1 = -1;
+    while (__any_sync(FULL, active)) {
+        const int x0 = max(cx - r, 0), x1 = min(cx + r, nx - 1);
+        const int y0 = max(cy - r, 0), y1 = min(cy + r, ny - 1);
+        const int z0 = max(cz - r, 0), z1 = min(cz + r, nz - 1);
+        const int e_end = (2 * r + 1) * (2 * r + 1);
+        // segments: two per old row (its new end cells), one per new row (all its cells)
+        const int nseg = active ? 2 * e_prev + (e_end - e_prev) : 0;
+        for (int s0 = 0; __any_sync(FULL, s0 < nseg); s0 += W) {
+            const float kth_now = key_dist(__shfl_sync(FULL, mine, K - 1, W));   // +inf until K were seen
+            const int sidx = s0 + sub;
+            int beg = 0, end = 0;
+            if (sidx < nseg) {
+                const bool old = sidx < 2 * e_prev;
+                const int e = old ? (sidx >> 1) : (sidx - e_prev);
+                const int z = cz + kRowOrder[e][0], y = cy + kRowOrder[e][1];
+                int a = x0, c = x1;   // cell range of this segment
+                if (old) {
+                    if (sidx & 1) a = px1 + 1;   // right end
+                    else c = px0 - 1;            // left end
+                }
+                if (z >= z0 && z <= z1 && y >= y0 && y <= y1 && a <= c) {
+                    // rows that cannot hold anything closer than the current K-th best are skipped
+                    const float dmin2 = slab_dist2(qy, Ps.lo[1], h, y, slack) + slab_dist2(qz, Ps.lo[2], h, z, slack);
+                    if (!(dmin2 > kth_now)) {
+                        const int row = (z * ny + y) * nx;
+                        beg = (row + a > 0) ? __ldg(cell_end + row + a - 1) : 0;
+                        end = __ldg(cell_end + row + c);
+                    }
+                }
+            }
+            const int cnt = end - beg;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < W; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, incl, o, W);
+                if (sub >= o) incl += u;
+            }
+            const int total = __shfl_sync(FULL, incl, W - 1, W);
+            const int excl = incl - cnt;
+            for (int j0 = 0; __any_sync(FULL, j0 < total); j0 += W) {
+                const int j = j0 + sub;
+                int seg = 0;   // number of segments of my group whose inclusive count is <= j
+#pragma unroll
+                for (int step = W / 2; step > 0; step >>= 1) {
+                    const int v = __shfl_sync(FULL, incl, seg + step - 1, W);
+                    if (v <= j) seg += step;
+                }
+                const int sb = __shfl_sync(FULL, beg, seg, W);
+                const int se = __shfl_sync(FULL, excl, seg, W);
+                key_t64 cand = KEY_INVALID;
+                if (j < total) {
+                    const float4 c = __ldg(sorted + sb + (j - se));
+                    cand = make_key(ref_sqdist(qx, qy, qz, c.x, c.y, c.z), __float_as_int(c.w));
+                }
+                // ---- offer the batch to the group's list; only candidates below its K-th entry matter
+                const key_t64 thr = __shfl_sync(FULL, mine, K - 1, W);
+                const unsigned ball = __ballot_sync(FULL, cand < thr);
+                unsigned mask = (W == 32) ? ball : ((ball >> (W * grp)) & ((1u << W) - 1u));
+                if (__any_sync(FULL, __popc(mask) > (3 * W) / 8)) {
+                    // many newcomers somewhere in the warp: sort the batch, keep the W smallest of list U batch
+                    group_sort<W>(cand, sub);
+                    const key_t64 rev = __shfl_sync(FULL, cand, W - 1 - sub, W);
+                    if (rev < mine) mine = rev;
+#pragma unroll
+                    for (int jj = W / 2; jj > 0; jj >>= 1) group_minmax<W>(mine, jj, (sub & jj) == 0);
+                    if (mine > KEY_EMPTY) mine = KEY_EMPTY;
+                } else {
+                    while (__any_sync(FULL, mask != 0)) {   // shift-insert one candidate per group
+                        const int src = mask ? __ffs(mask) - 1 : 0;
+                        key_t64 x = __shfl_sync(FULL, cand, src, W);
+                        if (!mask) x = KEY_INVALID;         // this group has nothing left: a no-op insert
+                        mask &= mask - 1;
+                        const key_t64 pred = __shfl_up_sync(FULL, mine, 1, W);
+                        if (x < mine) mine = (sub > 0 && x < pred) ? pred : x;   // mine sorts after x: shift or take x
+                    }
+                }
+            }
+        }
+        const float kth = key_dist(__shfl_sync(FULL, mine, K - 1, W));   // all lanes: shuffles stay warp-uniform
+        if (active) {
+            e_prev = e_end;
+            px0 = x0;
+            px1 = x1;
+            const float m = margin(r);
+            if (m == INF) {
+                done = true;
+                active = false;
+            } else {
+                const float ms = m - slack;
+                if (ms > 0.f && kth <= ms * ms * (1.0f - 1e-5f)) {
+                    done = true;
+                    active = false;
+                } else {
+                    // next ring: the K-th distance found so far bounds the true one, so jump to the
+                    // first block whose margin covers it
+                    int rn = r + 1;
+                    if (kth < INF) {
+                        const float need = sqrtf(kth) * (1.0f + 1e-4f) + slack;
+                        while (rn <= RMAX && margin(rn) < need) ++rn;
+                    }
+                    r = rn;
+                    active = r <= RMAX;
+                }
+            }
+        }
+    }
+    if (!valid) return;
+    if (done) {
+        if (sub < K) idx_out[((size_t)b * Q + q) * K + sub] = (IdxT)(unsigned)(mine & 0xffffffffu);
+        return;
+    }
+    if (sub == 0) {
+        QueryState *Pw = state_all + b;
+        const int rep = atomicCAS(&Pw->rep_q, 0, q + 1) - 1;   // stored as q+1: all-zero state = 'none'
+        bool dup = false;
+        if (rep != -1 && rep != q) {
+            const float *rp = query + ((size_t)b * Q + rep) * 3;
+            dup = (__ldg(rp) == qx) && (__ldg(rp + 1) == qy) && (__ldg(rp + 2) == qz);
+        }
+        if (dup) {
+            const int slot = atomicAdd(&Pw->dup_count, 1);
+            ovf_all[(size_t)b * Q + (Q - 1 - slot)] = q;
+        } else {
+            const int slot = atomicAdd(&Pw->ovf_count, 1);
+            ovf_all[(size_t)b * Q + slot] = q;
+        }
+    }
+}
+
 // ------------------------------------------------------------------ F. overflow: tiled full scan
 template <int KCAP, int THREADS, int TILE, typename IdxT>
 __global__ void __launch_bounds__(THREADS)
@@ -1005,7 +1249,15 @@ static int launch_search(const float *support, const float *query, int64_t B, in
     const bool self = (support == query) && (S == Q);
     const bool warp = K >= 2 && K <= 32 && !g_force_thread_search;
     FFB6D_CUDA(cudaMemsetAsync(qs.state, 0, (size_t)B * sizeof(QueryState), st));
-    if (warp) {
+    if (warp && K <= 16) {   // half a warp per query
+        dim3 ggrid((unsigned)ceil_div(Q, 16), (unsigned)B);
+        if (self)
+            grid_search_group_kernel<IdxT, true, 16><<<ggrid, 256, 0, st>>>(
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+        else
+            grid_search_group_kernel<IdxT, false, 16><<<ggrid, 256, 0, st>>>(
+                query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+    } else if (warp) {
         dim3 wgrid((unsigned)ceil_div(Q, 8), (unsigned)B);
         if (self)
             grid_search_warp_kernel<IdxT, true><<<wgrid, 256, 0, st>>>(
@@ -1065,25 +1317,11 @@ int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid
         set_error("knn grid build: %zu bytes of grid storage required, %zu given", w.bytes, grid_bytes);
         return FFB6D_ERR_WORKSPACE;
     }
-    FFB6D_CUDA(cudaMemsetAsync(w.ticket, 0, (size_t)B * sizeof(int), st));
-    int chunk = 8192;
-    if (ceil_div(S, chunk) > MAX_CHUNKS) chunk = (int)ceil_div(S, MAX_CHUNKS);
-    const int nchunks = (int)ceil_div(S, chunk);
-    grid_prepare_kernel<<<dim3((unsigned)nchunks, (unsigned)B), PREP_THREADS, 0, st>>>(
-        support, (int)S, K, chunk, nchunks, (int)w.maxc, (int)w.ntiles, K == 1 ? g_cell_scale_k1 : g_cell_scale, g_quantile,
-        w.params, w.ticket, w.partial);
-    FFB6D_LAUNCH_OK("grid_prepare_kernel");
-    dim3 tgrid((unsigned)w.ntiles, (unsigned)B);
-    grid_zero_kernel<<<tgrid, 256, 0, st>>>(w.params, w.cursor, w.maxc, w.tile_sum, (int)w.ntiles);
-    FFB6D_LAUNCH_OK("grid_zero_kernel");
-    dim3 pgrid((unsigned)ceil_div(S, 256), (unsigned)B);
-    grid_count_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, w.maxc, w.tile_sum,
-                                             (int)w.ntiles);
-    FFB6D_LAUNCH_OK("grid_count_kernel");
-    grid_scan_kernel<<<tgrid, 1024, 0, st>>>(w.params, w.cursor, w.maxc, w.tile_sum, (int)w.ntiles);
-    FFB6D_LAUNCH_OK("grid_scan_kernel");
-    grid_scatter_kernel<<<pgrid, 256, 0, st>>>(support, (int)S, w.params, w.cursor, w.maxc, w.sorted);
-    FFB6D_LAUNCH_OK("grid_scatter_kernel");
+    // one launch: a cluster of 8 CTAs per batch item (cluster dims are a compile-time attribute of the kernel)
+    grid_build_kernel<<<dim3(BUILD_CTAS, (unsigned)B), BUILD_THREADS, 0, st>>>(
+        support, (int)S, K, (int)w.maxc, K == 1 ? g_cell_scale_k1 : g_cell_scale, g_quantile, w.params, w.cursor,
+        w.rank, w.sorted);
+    FFB6D_LAUNCH_OK("grid_build_kernel");
     return FFB6D_OK;
 }
 
