@@ -599,6 +599,46 @@ def main():
         del mlps
         torch.cuda.empty_cache()
 
+    # ---- BASELINE configs[1] as ONE chained region: index build + the seven fusion stages (gathers + the 28
+    # fusion MLPs, p2r_fuse restructured as W1.rgb + (W2.p)[idx]) + final interpolation + choose gather
+    stack_line = None
+    if not args.no_mlp:
+        try:
+            from ffb6d_b200.pipeline import FusionStack
+            stack = FusionStack(B, n_points=N0, k=args.k, device=dev, seed=rank)
+
+            def full(restructured):
+                return stack(p.build_indices(cld_d, xyz_d, cho_d), restructured)
+
+            res = {}
+            for name_, flag in (("restructured", True), ("reference_order", False)):
+                run = p.capture(lambda flag=flag: full(flag)) if use_graph else (lambda flag=flag: full(flag))
+                for _ in range(2):
+                    run()
+                torch.cuda.synchronize()
+                t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                reps = max(3, min(steps, 10))
+                t0_.record()
+                for _ in range(reps):
+                    run()
+                t1_.record()
+                torch.cuda.synchronize()
+                res[name_] = t0_.elapsed_time(t1_) / reps
+                del run
+            stack_ms = res["restructured"]
+            stack_line = {"what": "BASELINE configs[1] chained: 22 KNN index builds + 7 fusion stages (16 gathers, 28 fusion "
+                                  "MLPs + 7 small W2.p products, the 7 p2r gathers folded into the p2r_fuse epilogue) + final "
+                                  "interpolation + choose gather, one CUDA graph per step",
+                          "ms_per_step": stack_ms, "value": world * B * N0 / (stack_ms / 1e3), "unit": UNIT,
+                          "reference_order_ms_per_step": res["reference_order"],
+                          "mlp_flops_per_step_reference": stack.flops,
+                          "note": "reference_order = the same kernels composed as the reference does (materialised "
+                                  "interpolated maps, p2r_fuse over 2*C_r channels)"}
+            del stack
+            torch.cuda.empty_cache()
+        except Exception as e:                      # noqa: BLE001
+            stack_line = {"error": str(e)[:300]}
+
     # ---- comparators on the same box.  C5: the reference's own torch expressions
     # (models/ffb6d.py:159-194, restated in _torch_cpu_random_sample) on THIS GPU with the same features and
     # int64 indices (train_ycb.py:224-232 casts them before the forward pass; the cast is not timed).
@@ -698,7 +738,7 @@ def main():
                              "enqueue a step" % (spin_ms / steps, enqueue_ms / steps),
         "digest_ok": digest_ok, "reference_digest_ok": reference_digest_ok,
         "roofline": roofline, "compute": compute, "pass_roofline": pass_roofline,
-        "fusion_mlps": mlp_line, "cpu_baseline": cpu_baseline, "gpu_torch_reference": gpu_torch,
+        "fusion_mlps": mlp_line, "fusion_stack": stack_line, "cpu_baseline": cpu_baseline, "gpu_torch_reference": gpu_torch,
         "host_api": host_api, "clocks": clocks,
     }
     emit(line)

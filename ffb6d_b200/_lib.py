@@ -48,6 +48,7 @@ def _load():
         "ffb6d_knn_grid_query_bytes": (sz, [i64, i64]),
         "ffb6d_knn_grid_build": (ci, [vp, i64, i64, ci, vp, sz, vp]),
         "ffb6d_knn_grid_query": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp, sz, vp]),
+        "ffb6d_knn_grid_query_organized": (ci, [vp, vp, i64, i64, i64, ci, vp, ci, vp, sz, vp, sz, i64, vp]),
         "ffb6d_build_indices_workspace_bytes": (sz, [i64, i64, i64, i64, ci]),
         "ffb6d_build_indices": (ci, [vp, vp, vp, vp, i64, i64, i64, i64, ci, vp, ci, vp, sz, vp]),
         "ffb6d_knn_grid_tune": (None, [fp, ci]),
@@ -65,6 +66,13 @@ def _load():
         "ffb6d_fusion_mlp_pack_bytes": (sz, [i64, i64]),
         "ffb6d_fusion_mlp_pack": (ci, [vp, i64, i64, vp, sz, vp]),
         "ffb6d_fusion_mlp_fwd_packed": (ci, [vp, i64, vp, i64, vp, vp, vp, i64, i64, i64, ci, fp, vp, vp]),
+        "ffb6d_fusion_mlp_fwd_ex": (ci, [vp, i64, vp, i64, vp, vp, vp, i64, i64, i64, ci, fp, vp, vp, ci, i64, ci, vp, vp]),
+        "ffb6d_bn_workspace_bytes": (sz, [i64, i64]),
+        "ffb6d_bn_train_fwd": (ci, [vp, i64, i64, i64, vp, vp, fp, fp, vp, vp, ci, fp, vp, vp, vp, sz, vp]),
+        "ffb6d_bn_train_bwd": (ci, [vp, vp, vp, i64, i64, i64, ci, fp, vp, vp, vp, vp, sz, vp]),
+        "ffb6d_act_bwd": (ci, [vp, vp, i64, ci, fp, vp, vp]),
+        "ffb6d_fusion_mlp_wgrad": (ci, [vp, vp, i64, vp, i64, i64, i64, i64, vp, vp]),
+        "ffb6d_att_pool_bwd": (ci, [vp, i64, vp, i64, vp, vp, i64, i64, ci, vp, vp, vp, vp]),
         "ffb6d_att_pool_fwd": (ci, [vp, i64, vp, i64, vp, i64, i64, ci, vp, vp]),
         "ffb6d_relative_pos_encoding_cm_fwd": (ci, [vp, vp, ci, i64, i64, ci, vp, vp]),
         "ffb6d_backproject": (ci, [vp, i64, i64, i64, vp, ci, vp, i64, vp, vp, vp, vp, vp]),

@@ -60,7 +60,6 @@ const Env &env()
         auto on = [](const char *n) { const char *x = getenv(n); return x && *x && strcmp(x, "0") != 0; };
         v.gather_direct = on("FFB6D_GATHER_DIRECT");
         v.mlp_no_direct = on("FFB6D_MLP_NO_DIRECT");
-        v.mlp_pair = on("FFB6D_MLP_PAIR");
         v.check_indices = on("FFB6D_CHECK_INDICES");
         v.grid_thread_search = on("FFB6D_GRID_THREAD_SEARCH");
         const char *x;
@@ -216,6 +215,21 @@ int ffb6d_knn_grid_query(const float *support, const float *query, int64_t B, in
     FFB6D_CHECK_ARG(support && query && idx_out && grid && scratch, "knn_grid_query: null pointer");
     return knn_grid_query(support, query, B, S, Q, K, idx_out, idx_is_i64, grid, grid_bytes, scratch,
                           scratch_bytes, (cudaStream_t)stream);
+}
+
+int ffb6d_knn_grid_query_organized(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
+                                   int K, void *idx_out, int idx_is_i64, const void *grid, size_t grid_bytes,
+                                   void *scratch, size_t scratch_bytes, int64_t query_width, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && S >= 1 && Q >= 0 && B < 65536 && S < (1ll << 31) && Q < (1ll << 31),
+                    "knn_grid_query: bad size");
+    FFB6D_CHECK_ARG(K >= 1 && K <= FFB6D_MAX_K, "knn_grid_query: K=%d outside [1,%d]", K, FFB6D_MAX_K);
+    FFB6D_CHECK_ARG(query_width >= 0 && (query_width == 0 || Q % query_width == 0),
+                    "knn_grid_query: query_width=%lld does not divide Q=%lld", (long long)query_width, (long long)Q);
+    if (B == 0 || Q == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(support && query && idx_out && grid && scratch, "knn_grid_query: null pointer");
+    return knn_grid_query(support, query, B, S, Q, K, idx_out, idx_is_i64, grid, grid_bytes, scratch,
+                          scratch_bytes, (cudaStream_t)stream, query_width);
 }
 
 void ffb6d_knn_grid_tune(float cell_scale, int quantile) { knn_grid_tune(cell_scale, quantile); }

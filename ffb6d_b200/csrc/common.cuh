@@ -75,7 +75,6 @@ static inline int num_sms() { return device_info().num_sms; }
 struct Env {
     bool gather_direct;     // FFB6D_GATHER_DIRECT=1: K-lane gathers through the older direct kernel
     bool mlp_no_direct;     // FFB6D_MLP_NO_DIRECT=1
-    bool mlp_pair;          // FFB6D_MLP_PAIR=1
     bool check_indices;     // FFB6D_CHECK_INDICES=1: validate gather indices (synchronises; debugging aid)
     bool grid_thread_search;
     float grid_scale, grid_scale_k1;

@@ -11,7 +11,6 @@
 //   fusion_mlp_packed_kernel  the product path: weights pre-split once (ffb6d_fusion_mlp_pack) and
 //                             fetched by bulk-async copies, warp-specialised mbarrier pipeline,
 //                             16 staging warps (K > 128) or the 3-CTA/SM DIRECT variant (K <= 128)
-//   fusion_mlp_pair_kernel    opt-in (FFB6D_MLP_PAIR=1): tcgen05.mma.cta_group::2, two CTAs per MMA
 //
 // All of them fuse the concat (two K ranges read from two tensors), the GEMM, BN and ReLU:
 //   * tcgen05.mma kind::tf32, M = N = 128 per CTA, accumulators in TMEM (128 lanes x 128 columns)
@@ -33,6 +32,7 @@
 //     point axis (NCHW output, no transposition needed because M = output channel = TMEM lane).
 #include "common.cuh"
 
+#include <algorithm>
 #include <stdlib.h>
 #include <type_traits>
 
@@ -115,6 +115,17 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 // register sums, so that two CTAs fit on an SM and one's prologue / epilogue overlaps the other's
 // main loop.
 constexpr int PACK_BLOCK_BYTES = 2 * TILE_BYTES;                 // A_hi + A_lo of one k-tile
+
+// Optional extras of the epilogue (all null / 0 for the plain layer):
+//   addend [B, NA, Co] (channels-last) + idx [B, P]: out = act(scale * (W x + addend[b, idx[b, p], :]) + shift)
+//   out_nsc: the result is stored channels-last, [B, P, Co]
+struct MlpEpilogue {
+    const float *addend;
+    const void *idx;
+    int NA;
+    int idx_is_i64;
+    int out_nsc;
+};
 constexpr int mlp2_threads(int nsw) { return (nsw + 2) * 32; }   // staging warps + producer + issuer
 constexpr int mlp2_smem(int nst) { return nst * STAGE_BYTES + 128; }
 
@@ -150,7 +161,7 @@ __global__ void __launch_bounds__(mlp2_threads(NSW), DIRECT ? 3 : 1)
 fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
                          const unsigned char *__restrict__ wpack, const float *__restrict__ scale,
                          const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
-                         float slope)
+                         float slope, MlpEpilogue ep)
 {
     extern __shared__ __align__(1024) unsigned char smem[];
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * STAGE_BYTES);
@@ -377,6 +388,12 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
         const bool row_ok = gm < Co;
         const float sc = row_ok ? __ldg(scale + gm) : 0.f, sh = row_ok ? __ldg(shift + gm) : 0.f;
         float *orow = out + ((size_t)b * Co + (row_ok ? gm : 0)) * P;
+        // optional epilogue extras (MlpEpilogue): a gathered addend in front of the affine -- the second half
+        // of a concat-GEMM restructured as W1*x + (W2*p)[idx] -- and a channels-last store
+        const float *add_row = ep.addend ? ep.addend + (size_t)b * ep.NA * Co + (row_ok ? gm : 0) : nullptr;
+        const int *idx32 = (ep.addend && !ep.idx_is_i64) ? reinterpret_cast<const int *>(ep.idx) + (size_t)b * P : nullptr;
+        const long long *idx64 = (ep.addend && ep.idx_is_i64) ? reinterpret_cast<const long long *>(ep.idx) + (size_t)b * P : nullptr;
+        float *ocol = ep.out_nsc ? out + (size_t)b * P * Co + (row_ok ? gm : 0) : nullptr;
 #pragma unroll
         for (int i = 0; i < NI; ++i) {
             uint32_t v[32];
@@ -392,12 +409,27 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                     const int gn = n0 + COLS * cs + 32 * i + j;
                     float y[4];
 #pragma unroll
+                    for (int u = 0; u < 4; ++u) y[u] = __uint_as_float(v[j + u]);
+                    if (add_row) {   // the column's index is the same for the whole warp (one broadcast load),
+                                     // the addend row is channels-last: 32 lanes read 128 contiguous bytes
+                        int a[4];
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            a[u] = (gn + u < P) ? (idx32 ? __ldg(idx32 + gn + u) : (int)__ldg(idx64 + gn + u)) : 0;
+#pragma unroll
+                        for (int u = 0; u < 4; ++u) y[u] = __fadd_rn(y[u], __ldg(add_row + (size_t)a[u] * Co));
+                    }
+#pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                        y[u] = __fadd_rn(__fmul_rn(__uint_as_float(v[j + u]), sc), sh);
+                        y[u] = __fadd_rn(__fmul_rn(y[u], sc), sh);
                         if (act == 1) y[u] = fmaxf(y[u], 0.f);
                         else if (act == 2) y[u] = (y[u] > 0.f) ? y[u] : __fmul_rn(y[u], slope);
                     }
-                    if (vec && gn + 3 < P) {
+                    if (ocol) {
+#pragma unroll
+                        for (int u = 0; u < 4; ++u)
+                            if (gn + u < P) ocol[(size_t)(gn + u) * Co] = y[u];
+                    } else if (vec && gn + 3 < P) {
                         *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
                     } else {
 #pragma unroll
@@ -414,265 +446,182 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
 }
 
 
-// ===================================================================== CTA-pair kernel (cta_group::2)
-// Layers with Co >= 256: two CTAs of a cluster (neighbouring 128-row tiles of W, the same 128
-// columns of X) run ONE tcgen05.mma.cta_group::2 of M = 256.  Each CTA brings its own A tile (TMA
-// bulk copy of its packed block) and only HALF of the B tile (64 of the 128 columns), so the
-// activation staging -- the instruction-bound part of the single-CTA kernel -- halves per SM; each
-// CTA's TMEM receives the accumulator rows of its own 128 output channels, which it drains and
-// stores exactly as before.  Synchronisation: staging warps arrive on their OWN CTA's full_b barrier
-// (a remote, cluster-scope arrive per warp and tile was measured to cost more than the staging it
-// saved); the peer's otherwise idle issuer lane waits for its CTA's two halves and forwards one
-// "stage ready" arrive to the leader (mapa + mbarrier.arrive.release.cluster); the leader's
-// tcgen05.commit is multicast to the empty / chunk barriers of both CTAs.
-constexpr int PAIR_NSW = 16, PAIR_NST = 4, PAIR_PD = 3;
-constexpr int PAIR_THREADS = (PAIR_NSW + 2) * 32;
-constexpr int PAIR_BCHUNK = 64 * 16;                             // a CTA holds 64 of the 128 B rows: compact K chunks
-constexpr int PAIR_BTILE = (TK / 4) * PAIR_BCHUNK;               // 8 KB
-constexpr int PAIR_STAGE = 2 * TILE_BYTES + 2 * PAIR_BTILE;      // A_hi, A_lo (16 KB each), B_hi, B_lo (8 KB each)
-constexpr int PAIR_SMEM = PAIR_NST * PAIR_STAGE + 256;
+// ===================================================================== weight gradient (training)
+// dW[co, ci] = sum_b sum_p dZ[b, co, p] * X[b, ci, p],  X = [X1; X2]  (backward of the 1x1 conv w.r.t. its
+// weight: a GEMM with M = Co, N = Ci and the long axis K = B * P).  Both operands are K-contiguous in memory
+// (dZ and X are NCHW: the point axis is the fast one), so every thread loads 16 bytes along K and writes one
+// whole (row; k..k+3) slot of the K-major UMMA layout -- no transposition.  Same numerics as the forward
+// layer: 3xTF32 split of both operands while they are staged, K accumulated in chunks of 128 into two
+// alternating TMEM accumulators that are drained into round-to-nearest fp32 register sums.  Split-K over
+// the grid's z axis: every CTA owns a run of (frame, 32-point) k-tiles and adds its 128x128 partial to dW
+// with fp32 atomics (dW is zero-filled by the entry point), like cuDNN's own wgrad: summation order is not
+// deterministic, values agree to fp32 round-off.
+constexpr int WG_SMEM = 2 * STAGE_BYTES + 64;
 
-__device__ __forceinline__ uint64_t umma_desc_pair_b(uint32_t saddr)
+__global__ void __launch_bounds__(256, 1)
+fusion_wgrad_kernel(const float *__restrict__ dz, const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
+                    float *__restrict__ dw, int Co, int P, int tiles_per_frame, int total_tiles, int tiles_per_split)
 {
-    return (uint64_t)((saddr & 0x3FFFF) >> 4) | ((uint64_t)(PAIR_BCHUNK >> 4) << 16) | ((uint64_t)(128 >> 4) << 32) | (1ull << 46);
-}
-constexpr uint32_t kIdescPair = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TN >> 3) << 17) | ((uint32_t)((2 * TM) >> 4) << 24);
-
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity)
-{
-    uint32_t done = 0;
-    for (int spin = 0; !done; ++spin) {
-        asm volatile(
-            "{\n\t.reg .pred P1;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2;\n\t"
-            "selp.b32 %0, 1, 0, P1;\n\t}\n"
-            : "=r"(done) : "r"(bar), "r"(parity) : "memory");
-        if (spin > (1 << 26)) __trap();
-    }
-}
-
-// arrive on the barrier at the same shared-memory offset in CTA `rank` of the cluster
-__device__ __forceinline__ void mbar_arrive_remote(uint32_t bar, uint32_t rank)
-{
-    asm volatile(
-        "{\n\t.reg .b32 ra;\n\tmapa.shared::cluster.u32 ra, %0, %1;\n\t"
-        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t}\n"
-        :: "r"(bar), "r"(rank) : "memory");
-}
-
-__device__ __forceinline__ void cluster_sync_all()
-{
-    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-
-__global__ void __launch_bounds__(PAIR_THREADS, 1)
-fusion_mlp_pair_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
-                       const unsigned char *__restrict__ wpack, const float *__restrict__ scale,
-                       const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
-                       float slope)
-{
-    constexpr int NST = PAIR_NST, NSW = PAIR_NSW, PD = PAIR_PD;
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * PAIR_STAGE);
-    uint64_t *full_a = bars, *full_b = bars + NST, *empty = bars + 2 * NST, *chunk = bars + 3 * NST;
-    uint64_t *peer_a = chunk + 2;   // leader only: the peer's halves of the stage are in place
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NST * PAIR_STAGE + 224);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * STAGE_BYTES);   // [0],[1]: stage free; [2],[3]: chunk done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + 2 * STAGE_BYTES + 48);
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    uint32_t rank;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
-    const bool leader = rank == 0;
-    const int mt = blockIdx.x, nt = blockIdx.y;   // the pair lies along x: a (1,2,1) cluster was refused by the launch
-    const int b = blockIdx.z, m0 = mt * TM, n0 = nt * TN;
-    const int nh = n0 + 64 * (int)rank;   // the 64 columns of X this CTA stages
+    const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
     const int Ci = C1 + C2;
-    const int nk = (Ci + TK - 1) / TK;
+    const int kt_begin = blockIdx.z * tiles_per_split, kt_end = min(total_tiles, kt_begin + tiles_per_split);
+    const int nk = kt_end - kt_begin;
+    if (nk <= 0) return;   // CTA-uniform
 
     if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(2 * TN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(2 * TN));
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 32) {
-        for (int i = 0; i < NST; ++i) {
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(full_a + i)));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(full_b + i)), "r"(NSW));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(empty + i)));
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(peer_a + i)));
-        }
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(chunk + 0)));
-        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(chunk + 1)));
+        for (int i = 0; i < 4; ++i)
+            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bars + i)));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    cluster_sync_all();   // both CTAs' barriers exist before anyone arrives remotely
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_d = *tmem_slot;
 
-    if (wid == NSW) {
-        // ---------------- A producer (every CTA loads the packed block of its own 128 rows)
-        if (lane == 0) {
-            const unsigned char *src = wpack + (size_t)mt * nk * PACK_BLOCK_BYTES;
-            for (int kt = 0; kt < nk; ++kt) {
-                const int st = kt % NST, n = kt / NST;
-                if (n >= 1) mbar_wait_cluster(smem_u32(empty + st), (uint32_t)((n - 1) & 1));
-                const uint32_t bar = smem_u32(full_a + st);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(PACK_BLOCK_BYTES) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(smem + st * PAIR_STAGE)), "l"(src + (size_t)kt * PACK_BLOCK_BYTES),
-                                "r"(PACK_BLOCK_BYTES), "r"(bar) : "memory");
-            }
-        }
-        __syncwarp();
-    } else if (wid == NSW + 1) {
-        if (lane == 0) {
-            if (leader) {
-                // ---------------- MMA issuer for the pair
-                for (int kt = 0; kt < nk; ++kt) {
-                    const int st = kt % NST, n = kt / NST;
-                    mbar_wait(smem_u32(full_a + st), (uint32_t)(n & 1));
-                    mbar_wait(smem_u32(full_b + st), (uint32_t)(n & 1));
-                    mbar_wait_cluster(smem_u32(peer_a + st), (uint32_t)(n & 1));
-                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    const uint32_t a_hi = smem_u32(smem + st * PAIR_STAGE);
-                    const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + TILE_BYTES);
-                    const uint64_t db_hi = umma_desc_pair_b(a_hi + 2 * TILE_BYTES);
-                    const uint64_t db_lo = umma_desc_pair_b(a_hi + 2 * TILE_BYTES + PAIR_BTILE);
-                    const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
-                    auto mma2 = [&](uint64_t da, uint64_t db, uint32_t accumulate) {
-                        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
-                                     "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}\n"
-                                     :: "r"(d_buf), "l"(da), "l"(db), "r"(kIdescPair), "r"(accumulate) : "memory");
-                    };
+    const bool vec = ((P & 3) == 0) && ((reinterpret_cast<uintptr_t>(dz) & 15) == 0) &&
+                     ((reinterpret_cast<uintptr_t>(x1) & 15) == 0) && (!x2 || (reinterpret_cast<uintptr_t>(x2) & 15) == 0);
+    const int q = wid & 3, half = wid >> 2;   // this thread's accumulator row = 32q + lane, columns 64*half ..
+    float acc[64];
 #pragma unroll
-                    for (int j = 0; j < TK / 8; ++j) {
-                        const uint64_t oa = (uint64_t)(j * ((2 * CHUNK_BYTES) >> 4)), ob = (uint64_t)(j * ((2 * PAIR_BCHUNK) >> 4));
-                        mma2(da_hi + oa, db_hi + ob, (kt % CH != 0 || j > 0) ? 1u : 0u);
-                        mma2(da_lo + oa, db_hi + ob, 1u);
-                        mma2(da_hi + oa, db_lo + ob, 1u);
-                    }
-                    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                 :: "r"(smem_u32(empty + st)), "h"((unsigned short)3) : "memory");
-                    if (kt % CH == CH - 1 || kt == nk - 1)
-                        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                                     :: "r"(smem_u32(chunk + ((kt / CH) & 1))), "h"((unsigned short)3) : "memory");
-                }
-            } else {
-                // ---------------- peer: tell the leader when this CTA's halves of the stage are in place
-                for (int kt = 0; kt < nk; ++kt) {
-                    const int st = kt % NST, n = kt / NST;
-                    mbar_wait(smem_u32(full_a + st), (uint32_t)(n & 1));
-                    mbar_wait(smem_u32(full_b + st), (uint32_t)(n & 1));
-                    mbar_arrive_remote(smem_u32(peer_a + st), 0u);
+    for (int i = 0; i < 64; ++i) acc[i] = 0.f;
+    auto drain = [&](int c) {
+        const int buf = c & 1;
+        mbar_wait(smem_u32(bars + 2 + buf), (uint32_t)((c >> 1) & 1));
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t v[16];
+            const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + 64 * half + 16 * i);
+            asm volatile(
+                "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+                "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+                : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                  "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+                : "r"(taddr));
+            asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+            for (int j = 0; j < 16; ++j) acc[16 * i + j] = __fadd_rn(acc[16 * i + j], __uint_as_float(v[j]));
+        }
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    };
+    // global -> registers: warp w stages K chunk w (4 points) of both operands; lanes take rows lane + 32*i
+    auto load_rows = [&](const float *base, int rows, int row0, int p0, float4 (&r)[4]) {
+        // base: [rows_total, P] of this frame; element (row, p0 + 4*wid .. +3)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int gr = row0 + lane + 32 * i, gp = p0 + 4 * wid;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gr < rows && gp < P) {
+                const float *src = base + (size_t)gr * P + gp;
+                if (vec && gp + 3 < P) {
+                    v = __ldg(reinterpret_cast<const float4 *>(src));
+                } else {
+                    v.x = __ldg(src);
+                    if (gp + 1 < P) v.y = __ldg(src + 1);
+                    if (gp + 2 < P) v.z = __ldg(src + 2);
+                    if (gp + 3 < P) v.w = __ldg(src + 3);
                 }
             }
+            r[i] = v;
         }
-        __syncwarp();
-    } else {
-        // ---------------- activation staging (64 columns), accumulator drain, epilogue
-        const float *xb1 = x1 + (size_t)b * C1 * P;
-        const float *xb2 = x2 ? x2 + (size_t)b * C2 * P : nullptr;
-        const bool vec = ((P & 3) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
-        constexpr int COLS = 4 * TN / NSW;                      // 32 accumulator columns per thread
-        const int q = wid & 3, cs = wid >> 2;
-        float acc[COLS];
+    };
+    auto load_tile = [&](int kt, float4 (&ra)[4], float4 (&rb)[4]) {
+        const int b = kt / tiles_per_frame, p0 = (kt % tiles_per_frame) * TK;
+        load_rows(dz + (size_t)b * Co * P, Co, m0, p0, ra);
+        // B rows = input channels n0 .. n0+127 of cat(x1, x2); a 128-row tile may straddle the concat
 #pragma unroll
-        for (int i = 0; i < COLS; ++i) acc[i] = 0.f;
-        auto drain = [&](int c) {
-            const int buf = c & 1;
-            mbar_wait_cluster(smem_u32(chunk + buf), (uint32_t)((c >> 1) & 1));
+        for (int i = 0; i < 4; ++i) {
+            const int gn = n0 + lane + 32 * i, gp = p0 + 4 * wid;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (gn < Ci && gp < P) {
+                const float *src = (gn < C1) ? x1 + ((size_t)b * C1 + gn) * P + gp : x2 + ((size_t)b * C2 + (gn - C1)) * P + gp;
+                if (vec && gp + 3 < P) {
+                    v = __ldg(reinterpret_cast<const float4 *>(src));
+                } else {
+                    v.x = __ldg(src);
+                    if (gp + 1 < P) v.y = __ldg(src + 1);
+                    if (gp + 2 < P) v.z = __ldg(src + 2);
+                    if (gp + 3 < P) v.w = __ldg(src + 3);
+                }
+            }
+            rb[i] = v;
+        }
+    };
+    auto store_tile = [&](int st, const float4 (&ra)[4], const float4 (&rb)[4]) {
+        unsigned char *sA_hi = smem + st * STAGE_BYTES, *sA_lo = sA_hi + TILE_BYTES;
+        unsigned char *sB_hi = sA_lo + TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
+        float4 hi, lo;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {   // a warp's 16-byte stores are contiguous: bank-conflict free
+            const int m = lane + 32 * i;
+            split4(ra[i], hi, lo);
+            *reinterpret_cast<float4 *>(sA_hi + wid * CHUNK_BYTES + m * 16) = hi;
+            *reinterpret_cast<float4 *>(sA_lo + wid * CHUNK_BYTES + m * 16) = lo;
+            split4(rb[i], hi, lo);
+            *reinterpret_cast<float4 *>(sB_hi + wid * CHUNK_BYTES + m * 16) = hi;
+            *reinterpret_cast<float4 *>(sB_lo + wid * CHUNK_BYTES + m * 16) = lo;
+        }
+    };
+
+    float4 ra[4], rb[4], na[4], nb[4];
+    load_tile(kt_begin, ra, rb);
+    for (int kt = 0; kt < nk; ++kt) {
+        const int st = kt & 1;
+        if (kt + 1 < nk) load_tile(kt_begin + kt + 1, na, nb);
+        if (kt >= 2) mbar_wait(smem_u32(bars + st), ((kt >> 1) - 1) & 1);   // MMAs that read this stage are done
+        store_tile(st, ra, rb);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+        __syncthreads();
+        if (tid == 0) {
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
+            const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + TILE_BYTES);
+            const uint64_t db_hi = umma_desc(a_hi + 2 * TILE_BYTES), db_lo = umma_desc(a_hi + 3 * TILE_BYTES);
+            const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
 #pragma unroll
-            for (int i = 0; i < COLS / 16; ++i) {
-                uint32_t v[16];
-                const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + COLS * cs + 16 * i);
-                asm volatile(
-                    "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-                    "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
-                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-                    : "r"(taddr));
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-                for (int j = 0; j < 16; ++j) acc[16 * i + j] = __fadd_rn(acc[16 * i + j], __uint_as_float(v[j]));
+            for (int j = 0; j < TK / 8; ++j) {
+                const uint64_t off = (uint64_t)(j * ((2 * CHUNK_BYTES) >> 4));
+                umma_tf32(d_buf, da_hi + off, db_hi + off, (kt % CH != 0 || j > 0) ? 1u : 0u);
+                umma_tf32(d_buf, da_lo + off, db_hi + off, 1u);
+                umma_tf32(d_buf, da_hi + off, db_lo + off, 1u);
             }
-            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-        };
-        // X half tile (32 k x 64 n): warp -> K chunk kg (4 k rows) and 32 of the 64 columns; a lane owns
-        // one column: four scalar loads (coalesced along n) make one whole 16-byte (n; k..k+3) slot
-        const int kg = wid & 7, nl = 32 * (wid >> 3) + lane;
-        const bool fast = ((C1 & 3) == 0) && (nh + 64 <= P);   // a K chunk never straddles the concat, columns in range
-        auto load_b = [&](int kt, float (&rb)[4]) {
-            const int gn = nh + nl;
-            const int gk0 = kt * TK + 4 * kg;
-            if (fast && gk0 + 3 < Ci) {
-                const float *p0 = ((gk0 < C1) ? xb1 + (size_t)gk0 * P : xb2 + (size_t)(gk0 - C1) * P) + gn;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) rb[j] = __ldg(p0 + (size_t)j * P);
-                return;
-            }
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                const int gk = kt * TK + 4 * kg + j;
-                float v = 0.f;
-                if (gk < Ci && gn < P) v = __ldg(((gk < C1) ? xb1 + (size_t)gk * P : xb2 + (size_t)(gk - C1) * P) + gn);
-                rb[j] = v;
-            }
-        };
-        auto store_b = [&](int st, const float (&rb)[4]) {
-            unsigned char *sB_hi = smem + st * PAIR_STAGE + 2 * TILE_BYTES, *sB_lo = sB_hi + PAIR_BTILE;
-            float4 hi, lo;
-            split4(make_float4(rb[0], rb[1], rb[2], rb[3]), hi, lo);
-            *reinterpret_cast<float4 *>(sB_hi + kg * PAIR_BCHUNK + nl * 16) = hi;   // 16-byte lane stride: conflict free
-            *reinterpret_cast<float4 *>(sB_lo + kg * PAIR_BCHUNK + nl * 16) = lo;
-        };
-        float ring[PD][4];
-#pragma unroll
-        for (int d = 0; d < PD; ++d)
-            if (d < nk) load_b(d, ring[d]);
-        for (int kt0 = 0; kt0 < nk; kt0 += PD) {
-#pragma unroll
-            for (int d = 0; d < PD; ++d) {
-                const int kt = kt0 + d;
-                if (kt < nk) {
-                    const int st = kt % NST, n = kt / NST;
-                    if (n >= 1) mbar_wait_cluster(smem_u32(empty + st), (uint32_t)((n - 1) & 1));
-                    store_b(st, ring[d]);
-                    if (kt + PD < nk) load_b(kt + PD, ring[d]);
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(smem_u32(full_b + st));
-                    if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
-                }
-            }
+            asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                         :: "r"(smem_u32(bars + st)) : "memory");
+            if (kt % CH == CH - 1 || kt == nk - 1)
+                asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
+                             :: "r"(smem_u32(bars + 2 + ((kt / CH) & 1))) : "memory");
         }
-        drain((nk - 1) / CH);
+        if (kt % CH == 0 && kt > 0) drain(kt / CH - 1);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            ra[i] = na[i];
+            rb[i] = nb[i];
+        }
+    }
+    drain((nk - 1) / CH);
+    {
         const int gm = m0 + 32 * q + lane;
         if (gm < Co) {
-            const float sc = __ldg(scale + gm), sh = __ldg(shift + gm);
-            float *orow = out + ((size_t)b * Co + gm) * P;
+            float *row = dw + (size_t)gm * Ci;
 #pragma unroll
-            for (int j = 0; j < COLS; j += 4) {
-                const int gn = n0 + COLS * cs + j;
-                float y[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    y[u] = __fadd_rn(__fmul_rn(acc[j + u], sc), sh);
-                    if (act == 1) y[u] = fmaxf(y[u], 0.f);
-                    else if (act == 2) y[u] = (y[u] > 0.f) ? y[u] : __fmul_rn(y[u], slope);
-                }
-                if (vec && gn + 3 < P) {
-                    *reinterpret_cast<float4 *>(orow + gn) = make_float4(y[0], y[1], y[2], y[3]);
-                } else {
-#pragma unroll
-                    for (int u = 0; u < 4; ++u)
-                        if (gn + u < P) orow[gn + u] = y[u];
-                }
+            for (int j = 0; j < 64; ++j) {
+                const int gn = n0 + 64 * half + j;
+                if (gn < Ci) atomicAdd(row + gn, acc[j]);
             }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    cluster_sync_all();   // nobody leaves (or frees TMEM) while the other CTA may still touch this one
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(2 * TN));
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(2 * TN));
 }
 
 }  // namespace ffb6d
@@ -715,53 +664,48 @@ extern "C" int ffb6d_fusion_mlp_pack(const float *weight, int64_t Co, int64_t Ci
     return FFB6D_OK;
 }
 
-extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const float *x2, int64_t C2, const void *packed,
-                                           const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
-                                           int act, float negative_slope, float *out, ffb6d_stream_t stream)
+extern "C" int ffb6d_fusion_mlp_fwd_ex(const float *x1, int64_t C1, const float *x2, int64_t C2, const void *packed,
+                                       const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
+                                       int act, float negative_slope, const float *addend, const void *add_idx,
+                                       int add_idx_is_i64, int64_t NA, int out_layout, float *out, ffb6d_stream_t stream)
 {
     const int rc = mlp_check(x1, C1, x2, C2, packed, scale, shift, B, Co, P, act, out);
     if (rc != FFB6D_OK) return rc > 0 ? FFB6D_OK : rc;
+    FFB6D_CHECK_ARG(out_layout == FFB6D_LAYOUT_NCS || out_layout == FFB6D_LAYOUT_NSC, "fusion_mlp_fwd: unknown out_layout %d",
+                    out_layout);
+    FFB6D_CHECK_ARG((addend == nullptr) == (add_idx == nullptr), "fusion_mlp_fwd: addend and add_idx come together");
+    FFB6D_CHECK_ARG(!addend || (NA >= 1 && NA < (1ll << 31)), "fusion_mlp_fwd: bad addend length");
     {
         auto k_big = fusion_mlp_packed_kernel<3, false, 16, 3>;
         auto k_direct = fusion_mlp_packed_kernel<1, true, 8, 2>;
         FFB6D_OPTIN_SMEM(k_big, mlp2_smem(3));
         FFB6D_OPTIN_SMEM(k_direct, mlp2_smem(1));
     }
+    MlpEpilogue ep;
+    ep.addend = addend;
+    ep.idx = add_idx;
+    ep.NA = (int)NA;
+    ep.idx_is_i64 = add_idx_is_i64;
+    ep.out_nsc = out_layout == FFB6D_LAYOUT_NSC;
     dim3 grid((unsigned)ceil_div(P, TN), (unsigned)ceil_div(Co, TM), (unsigned)B);
-    const bool no_direct = env().mlp_no_direct;
-    // opt-in (FFB6D_MLP_PAIR=1): validated, but at present ~10 % slower than the single-CTA kernel on the
-    // large layers (cluster-scope barrier round trips per stage)
-    const bool pair = env().mlp_pair;
-    if (pair && grid.y % 2 == 0 && grid.x <= 65535 && ceil_div(C1 + C2, TK) > CH) {
-        FFB6D_OPTIN_SMEM(fusion_mlp_pair_kernel, PAIR_SMEM);
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(grid.y, grid.x, grid.z);   // x = 128-row tile of W (pairs), y = 128-column tile of X
-        cfg.blockDim = dim3(PAIR_THREADS);
-        cfg.dynamicSmemBytes = PAIR_SMEM;
-        cfg.stream = (cudaStream_t)stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        FFB6D_CUDA(cudaLaunchKernelEx(&cfg, fusion_mlp_pair_kernel, x1, (int)C1, (const float *)(C2 ? x2 : nullptr), (int)C2,
-                                      (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P, act,
-                                      negative_slope));
-        count_launch();
-        return FFB6D_OK;
-    }
-    if (ceil_div(C1 + C2, TK) <= CH && !no_direct)
+    if (ceil_div(C1 + C2, TK) <= CH && !env().mlp_no_direct)
         fusion_mlp_packed_kernel<1, true, 8, 2><<<grid, mlp2_threads(8), mlp2_smem(1), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
-            act, negative_slope);
+            act, negative_slope, ep);
     else
         fusion_mlp_packed_kernel<3, false, 16, 3><<<grid, mlp2_threads(16), mlp2_smem(3), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
-            act, negative_slope);
+            act, negative_slope, ep);
     FFB6D_LAUNCH_OK("fusion_mlp_packed_kernel");
     return FFB6D_OK;
+}
+
+extern "C" int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const float *x2, int64_t C2, const void *packed,
+                                           const float *scale, const float *shift, int64_t B, int64_t Co, int64_t P,
+                                           int act, float negative_slope, float *out, ffb6d_stream_t stream)
+{
+    return ffb6d_fusion_mlp_fwd_ex(x1, C1, x2, C2, packed, scale, shift, B, Co, P, act, negative_slope, nullptr, nullptr, 0,
+                                   0, FFB6D_LAYOUT_NCS, out, stream);
 }
 
 extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2, int64_t C2, const float *weight,
@@ -790,4 +734,32 @@ extern "C" int ffb6d_fusion_mlp_fwd(const float *x1, int64_t C1, const float *x2
         r = ffb6d_fusion_mlp_fwd_packed(x1, C1, x2, C2, scratch, scale, shift, B, Co, P, act, negative_slope, out, stream);
     cudaFreeAsync(scratch, (cudaStream_t)stream);
     return r;
+}
+
+extern "C" int ffb6d_fusion_mlp_wgrad(const float *grad_z, const float *x1, int64_t C1, const float *x2, int64_t C2,
+                                      int64_t B, int64_t Co, int64_t P, float *grad_w, ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && C1 >= 1 && C2 >= 0 && Co >= 1 && P >= 0, "fusion_mlp_wgrad: bad size");
+    FFB6D_CHECK_ARG(B < 65536 && Co <= 65535ll * TM && C1 + C2 <= 65535ll * TN && P < (1ll << 31),
+                    "fusion_mlp_wgrad: size too large");
+    FFB6D_CHECK_ARG(grad_w, "fusion_mlp_wgrad: null grad_w");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t Ci = C1 + C2;
+    FFB6D_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)Co * Ci * sizeof(float), st));
+    if (B == 0 || P == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(grad_z && x1 && (C2 == 0 || x2), "fusion_mlp_wgrad: null pointer");
+    FFB6D_OPTIN_SMEM(fusion_wgrad_kernel, WG_SMEM);
+    const int64_t tpf = ceil_div(P, TK), total = B * tpf;
+    FFB6D_CHECK_ARG(total < (1ll << 31), "fusion_mlp_wgrad: B * P too large");
+    const int64_t tiles = ceil_div(Ci, TN) * ceil_div(Co, TM);
+    // split K so that the grid fills the SMs about twice, but keep at least 8 k-tiles (one chunk pair) per CTA
+    int64_t splits = std::max<int64_t>(1, std::min<int64_t>(ceil_div(2 * (int64_t)num_sms(), tiles), ceil_div(total, 8)));
+    if (splits > 65535) splits = 65535;
+    const int64_t per = ceil_div(total, splits);
+    splits = ceil_div(total, per);
+    dim3 grid((unsigned)ceil_div(Ci, TN), (unsigned)ceil_div(Co, TM), (unsigned)splits);
+    fusion_wgrad_kernel<<<grid, 256, WG_SMEM, st>>>(grad_z, x1, (int)C1, C2 ? x2 : nullptr, (int)C2, grad_w, (int)Co, (int)P,
+                                                    (int)tpf, (int)total, (int)per);
+    FFB6D_LAUNCH_OK("fusion_wgrad_kernel");
+    return FFB6D_OK;
 }

@@ -94,6 +94,6 @@ int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid
                    size_t grid_bytes, cudaStream_t st);
 int knn_grid_query(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
                    void *idx_out, int idx_is_i64, const void *grid_mem, size_t grid_bytes,
-                   void *scratch, size_t scratch_bytes, cudaStream_t st);
+                   void *scratch, size_t scratch_bytes, cudaStream_t st, int64_t query_width = 0);
 
 }  // namespace ffb6d

@@ -499,47 +499,24 @@ __device__ __forceinline__ float slab_dist2(float q, float lo, float h, int c, f
 }
 
 // ------------------------------------------------------------------ E. search
-template <int KCAP, typename IdxT, bool SELF>
-__global__ void __launch_bounds__(128)
-grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
-                   const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
-                   size_t cursor_stride, const float4 *__restrict__ sorted_all,
-                   IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
+// One query, one thread: scan the (2r+1)^3 block of cells around the query, r = 1..RMAX (each ring
+// adds only its shell), keeping a sorted top-K in registers.  Returns true when the K-th distance is
+// provably smaller than the distance to anything outside the scanned block.
+template <int KCAP>
+__device__ __forceinline__ bool thread_search(float qx, float qy, float qz, int K, const GridParams &Ps,
+                                              const int *__restrict__ cell_end, const float4 *__restrict__ sorted,
+                                              TopK<KCAP> &top)
 {
-    const int b = blockIdx.y;
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= Q) return;
-    const GridParams Ps = params_all[b];   // 64 B, same address for the whole CTA: L1 broadcast
-    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
-    const float4 *sorted = sorted_all + (size_t)b * S;
-    float qx, qy, qz;
-    int q;   // row of the output this thread produces
-    if (SELF) {  // queries are the support itself: walk them in cell order (coherent warps)
-        const float4 me = sorted[t];
-        qx = me.x;
-        qy = me.y;
-        qz = me.z;
-        q = __float_as_int(me.w);
-    } else {
-        const float *qp = query + ((size_t)b * Q + t) * 3;
-        qx = __ldg(qp);
-        qy = __ldg(qp + 1);
-        qz = __ldg(qp + 2);
-        q = t;
-    }
     const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
     const float h = Ps.h, slack = Ps.slack;
     const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
     const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
     const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
     const float INF = __int_as_float(0x7f800000);
-
     // a query further than RMAX cells outside the support's box cannot be certified by any block
     const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
                             fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
     bool done = false;
-    TopK<KCAP> top;
-    top.init();
     auto scan_range = [&](int beg, int end) {
         for (int p = beg; p < end; p += 4) {   // four loads in flight per thread
             float4 c[4];
@@ -600,15 +577,14 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
             done = ms > 0.f && kth <= ms * ms * (1.0f - 1e-5f);
         }
     }
-    if (done) {
-        IdxT *o = idx_out + ((size_t)b * Q + q) * K;
-#pragma unroll
-        for (int j = 0; j < KCAP; ++j)
-            if (j < K) o[j] = (IdxT)top.i[j];
-        return;
-    }
-    // not certified: hand over to the full scan, unless this query is bit-identical to the
-    // item's first far query (then it only needs a copy of that query's row)
+    return done;
+}
+
+// Not certified: hand the query over to the full scan, unless it is bit-identical to the item's first
+// far query (then it only needs a copy of that query's row).  Called by any subset of a warp's lanes.
+__device__ __forceinline__ void register_overflow(const float *__restrict__ query, int Q, int b, int q, float qx, float qy,
+                                                  float qz, QueryState *state_all, int *__restrict__ ovf_all)
+{
     QueryState *Pw = state_all + b;
     int rep = *(volatile int *)&Pw->rep_q;            // stored as q+1 so that all-zero means 'none'
     if (rep == 0) rep = atomicCAS(&Pw->rep_q, 0, q + 1);
@@ -634,6 +610,206 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
         const int slot = g.shfl(base, 0) + (int)g.thread_rank();
         ovf_all[(size_t)b * Q + slot] = q;
     }
+}
+
+template <int KCAP, typename IdxT, bool SELF>
+__global__ void __launch_bounds__(128)
+grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
+                   const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
+                   size_t cursor_stride, const float4 *__restrict__ sorted_all,
+                   IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
+{
+    const int b = blockIdx.y;
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= Q) return;
+    const GridParams Ps = params_all[b];   // 64 B, same address for the whole CTA: L1 broadcast
+    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
+    const float4 *sorted = sorted_all + (size_t)b * S;
+    float qx, qy, qz;
+    int q;   // row of the output this thread produces
+    if (SELF) {  // queries are the support itself: walk them in cell order (coherent warps)
+        const float4 me = sorted[t];
+        qx = me.x;
+        qy = me.y;
+        qz = me.z;
+        q = __float_as_int(me.w);
+    } else {
+        const float *qp = query + ((size_t)b * Q + t) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+        q = t;
+    }
+    TopK<KCAP> top;
+    top.init();
+    if (thread_search<KCAP>(qx, qy, qz, K, Ps, cell_end, sorted, top)) {
+        IdxT *o = idx_out + ((size_t)b * Q + q) * K;
+#pragma unroll
+        for (int j = 0; j < KCAP; ++j)
+            if (j < K) o[j] = (IdxT)top.i[j];
+        return;
+    }
+    register_overflow(query, Q, b, q, qx, qy, qz, state_all, ovf_all);
+}
+
+// ------------------------------------------------------------------ E0. K = 1, ORGANISED queries: one warp per 8x4 pixel tile
+// The p2r searches of the schedule ask for the nearest cloud point of every pixel of an image pyramid
+// level (ycb_dataset.py:291-293, 305-308): 94 % of all K = 1 queries.  Neighbouring pixels are
+// neighbouring points, so the 32 queries of an 8 x 4 pixel tile share ONE candidate set: the cells of
+// the bounding box of their own cells, grown by one cell.  All lanes walk the same candidate list
+// (warp-uniform addresses: one L1 broadcast per candidate, no divergence -- the thread-per-query kernel
+// runs at 14.5 of 32 lanes active) and certify their own result against the distance to the box faces.
+// The few lanes that cannot be certified (near depth discontinuities, box too large) are compacted per
+// CTA and finished by the per-thread ring search; hole pixels (far outside the support) go straight to
+// the overflow list as before.
+template <typename IdxT>
+__global__ void __launch_bounds__(256, 4)
+grid_search_k1_tile_kernel(const float *__restrict__ query, int S, int Q, int qw,
+                           const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
+                           size_t cursor_stride, const float4 *__restrict__ sorted_all,
+                           IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
+{
+    constexpr int TW = 8, TH = 4;               // tile = 8 x 4 pixels
+    constexpr int MAX_ROWS = 32, MAX_X = 8;     // widest shared box: 32 cell rows of up to 8 cells
+    constexpr int TILE_CAND = 128;              // candidates staged per round and warp
+    __shared__ float4 s_cand[8][TILE_CAND];
+    __shared__ int s_list[256];
+    __shared__ int s_count;
+    const unsigned FULL = 0xffffffffu;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int qh = Q / qw;
+    const int tiles_x = (qw + TW - 1) / TW, tiles_y = (qh + TH - 1) / TH;
+    const int tile = blockIdx.x * 8 + wid;
+    const GridParams Ps = params_all[b];
+    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
+    const float4 *sorted = sorted_all + (size_t)b * S;
+    const float INF = __int_as_float(0x7f800000);
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+
+    const int px = (tile % tiles_x) * TW + (lane & (TW - 1)), py = (tile / tiles_x) * TH + lane / TW;
+    const bool inimg = tile < tiles_x * tiles_y && px < qw && py < qh;
+    const int q = inimg ? py * qw + px : 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (inimg) {
+        const float *qp = query + ((size_t)b * Q + q) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+    }
+    const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
+    const float h = Ps.h, slack = Ps.slack;
+    const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
+                            fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
+    // state: 0 answered, 1 finish with the ring search, 2 overflow (far from the support), 3 no query
+    int state = !inimg ? 3 : ((out > (float)RMAX * h || !(qx == qx && qy == qy && qz == qz)) ? 2 : 1);
+    const bool part = state == 1;
+    const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
+    const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
+    const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
+    const int big = 0x3fffffff;
+    int X0 = __reduce_min_sync(FULL, part ? cx : big), X1 = __reduce_max_sync(FULL, part ? cx : -1);
+    int Y0 = __reduce_min_sync(FULL, part ? cy : big), Y1 = __reduce_max_sync(FULL, part ? cy : -1);
+    int Z0 = __reduce_min_sync(FULL, part ? cz : big), Z1 = __reduce_max_sync(FULL, part ? cz : -1);
+    if (X1 >= 0) {   // warp-uniform: somebody takes part
+        X0 = max(X0 - 1, 0); X1 = min(X1 + 1, nx - 1);
+        Y0 = max(Y0 - 1, 0); Y1 = min(Y1 + 1, ny - 1);
+        Z0 = max(Z0 - 1, 0); Z1 = min(Z1 + 1, nz - 1);
+        const int by = Y1 - Y0 + 1, nrows = by * (Z1 - Z0 + 1);
+        if (nrows <= MAX_ROWS && X1 - X0 + 1 <= MAX_X) {
+            int beg = 0, end = 0;
+            if (lane < nrows) {   // lane r looks up cell row r of the box
+                const int row = ((Z0 + lane / by) * ny + (Y0 + lane % by)) * nx;
+                beg = (row + X0 > 0) ? __ldg(cell_end + row + X0 - 1) : 0;
+                end = __ldg(cell_end + row + X1);
+            }
+            // the rows' point ranges are flattened (warp prefix sum) and the candidates staged in shared
+            // memory 128 at a time by all lanes in parallel; then every lane walks the same staged list
+            // (broadcast LDS.128): no per-row loop overhead, no divergence
+            const int cnt = end - beg;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int excl = incl - cnt;
+            float4 *stage = s_cand[wid];
+            float bd = INF;
+            int bi = 0;
+            for (int c0 = 0; c0 < total; c0 += TILE_CAND) {
+                const int n = min(TILE_CAND, total - c0);
+                __syncwarp();
+#pragma unroll
+                for (int u = 0; u < TILE_CAND / 32; ++u) {
+                    const int j = c0 + u * 32 + lane;
+                    int seg = 0;   // number of rows whose inclusive count is <= j
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, seg + step - 1);
+                        if (v <= j) seg += step;
+                    }
+                    const int sb = __shfl_sync(FULL, beg, seg & 31), se = __shfl_sync(FULL, excl, seg & 31);
+                    if (j < total) stage[u * 32 + lane] = __ldg(sorted + sb + (j - se));
+                }
+                __syncwarp();
+                for (int p = 0; p < n; p += 4) {
+                    float4 c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[u] = stage[min(p + u, n - 1)];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const float d = ref_sqdist(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+                        const int id = __float_as_int(c[u].w);
+                        if (p + u < n && (d < bd || (d == bd && id < bi))) {
+                            bd = d;
+                            bi = id;
+                        }
+                    }
+                }
+            }
+            if (part) {
+                // distance to the nearest face of the box that still has cells behind it
+                float m = INF;
+                if (X0 > 0) m = fminf(m, qx - (Ps.lo[0] + (float)X0 * h));
+                if (X1 < nx - 1) m = fminf(m, (Ps.lo[0] + (float)(X1 + 1) * h) - qx);
+                if (Y0 > 0) m = fminf(m, qy - (Ps.lo[1] + (float)Y0 * h));
+                if (Y1 < ny - 1) m = fminf(m, (Ps.lo[1] + (float)(Y1 + 1) * h) - qy);
+                if (Z0 > 0) m = fminf(m, qz - (Ps.lo[2] + (float)Z0 * h));
+                if (Z1 < nz - 1) m = fminf(m, (Ps.lo[2] + (float)(Z1 + 1) * h) - qz);
+                const float ms = m - slack;
+                const bool ok = (m == INF) ? (bd < INF || S == 0) : (ms > 0.f && bd <= ms * ms * (1.0f - 1e-5f));
+                if (ok) {
+                    idx_out[(size_t)b * Q + q] = (IdxT)bi;
+                    state = 0;
+                }
+            }
+        }
+    }
+    // ---- the uncertified queries of the CTA, compacted, finished by the per-thread ring search
+    if (state == 1) s_list[atomicAdd(&s_count, 1)] = q;
+    __syncthreads();
+    const int n_retry = s_count;
+    int q2 = -1;
+    float rx = 0.f, ry = 0.f, rz = 0.f;
+    bool retry_failed = false;
+    if ((int)threadIdx.x < n_retry) {
+        q2 = s_list[threadIdx.x];
+        const float *qp = query + ((size_t)b * Q + q2) * 3;
+        rx = __ldg(qp);
+        ry = __ldg(qp + 1);
+        rz = __ldg(qp + 2);
+        TopK<1> top;
+        top.init();
+        if (thread_search<1>(rx, ry, rz, 1, Ps, cell_end, sorted, top))
+            idx_out[(size_t)b * Q + q2] = (IdxT)top.i[0];
+        else
+            retry_failed = true;
+    }
+    if (retry_failed) register_overflow(query, Q, b, q2, rx, ry, rz, state_all, ovf_all);
+    if (state == 2) register_overflow(query, Q, b, q, qx, qy, qz, state_all, ovf_all);
 }
 
 // ------------------------------------------------------------------ E'. search, one WARP per query
@@ -898,7 +1074,7 @@ __device__ __forceinline__ void group_sort(key_t64 &k, int sub)   // ascending b
 }
 
 template <typename IdxT, bool SELF, int W>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, 5)
 grid_search_group_kernel(const float *__restrict__ query, int S, int Q, int K,
                          const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
                          size_t cursor_stride, const float4 *__restrict__ sorted_all,
@@ -1243,13 +1419,20 @@ void knn_grid_tune_k1(float cell_scale_k1)
 
 template <int KCAP, typename IdxT>
 static int launch_search(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
-                         int K, void *idx_out, const GridStore &w, const QueryScratch &qs,
+                         int K, void *idx_out, const GridStore &w, const QueryScratch &qs, int64_t query_width,
                          cudaStream_t st)
 {
     const bool self = (support == query) && (S == Q);
     const bool warp = K >= 2 && K <= 32 && !g_force_thread_search;
     FFB6D_CUDA(cudaMemsetAsync(qs.state, 0, (size_t)B * sizeof(QueryState), st));
-    if (warp && K <= 16) {   // half a warp per query
+    const bool organised = K == 1 && !self && query_width >= 8 && Q % query_width == 0 && Q / query_width >= 4 &&
+                           !g_force_thread_search;
+    if (organised) {   // queries are an image: one warp per 8x4 pixel tile
+        const int64_t tiles = ceil_div(query_width, 8) * ceil_div(Q / query_width, 4);
+        dim3 tgrid((unsigned)ceil_div(tiles, 8), (unsigned)B);
+        grid_search_k1_tile_kernel<IdxT><<<tgrid, 256, 0, st>>>(
+            query, (int)S, (int)Q, (int)query_width, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+    } else if (warp && K <= 16) {   // half a warp per query
         dim3 ggrid((unsigned)ceil_div(Q, 16), (unsigned)B);
         if (self)
             grid_search_group_kernel<IdxT, true, 16><<<ggrid, 256, 0, st>>>(
@@ -1296,15 +1479,15 @@ static int launch_search(const float *support, const float *query, int64_t B, in
 
 template <typename IdxT>
 static int launch_search_k(const float *support, const float *query, int64_t B, int64_t S, int64_t Q,
-                           int K, void *idx_out, const GridStore &w, const QueryScratch &qs,
+                           int K, void *idx_out, const GridStore &w, const QueryScratch &qs, int64_t query_width,
                            cudaStream_t st)
 {
-    if (K == 1) return launch_search<1, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
-    if (K <= 4) return launch_search<4, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
-    if (K <= 8) return launch_search<8, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
-    if (K <= 16) return launch_search<16, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
-    if (K <= 32) return launch_search<32, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
-    return launch_search<64, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    if (K == 1) return launch_search<1, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
+    if (K <= 4) return launch_search<4, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
+    if (K <= 8) return launch_search<8, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
+    if (K <= 16) return launch_search<16, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
+    if (K <= 32) return launch_search<32, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
+    return launch_search<64, IdxT>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
 }
 
 // Build the grid of `support` for searches of about K neighbours (K only tunes the cell size).
@@ -1328,7 +1511,7 @@ int knn_grid_build(const float *support, int64_t B, int64_t S, int K, void *grid
 // Search a built grid.  `support` must be the array the grid was built from.
 int knn_grid_query(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,
                    void *idx_out, int idx_is_i64, const void *grid_mem, size_t grid_bytes,
-                   void *scratch, size_t scratch_bytes, cudaStream_t st)
+                   void *scratch, size_t scratch_bytes, cudaStream_t st, int64_t query_width)
 {
     read_env();
     GridStore w = carve_grid(const_cast<void *>(grid_mem), B, S);
@@ -1338,8 +1521,8 @@ int knn_grid_query(const float *support, const float *query, int64_t B, int64_t 
                   scratch_bytes, qs.bytes);
         return FFB6D_ERR_WORKSPACE;
     }
-    if (idx_is_i64) return launch_search_k<long long>(support, query, B, S, Q, K, idx_out, w, qs, st);
-    return launch_search_k<int>(support, query, B, S, Q, K, idx_out, w, qs, st);
+    if (idx_is_i64) return launch_search_k<long long>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
+    return launch_search_k<int>(support, query, B, S, Q, K, idx_out, w, qs, query_width, st);
 }
 
 int knn_grid_launch(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, int K,

@@ -156,7 +156,7 @@ extern "C" int ffb6d_build_indices(const float *cld, const float *img2, const fl
             int rc;
             if (use_grid)
                 rc = knn_grid_query(sup, qry, B, S, Q, d.K, out[j], idx_is_i64, grid, knn_grid_store_bytes(B, S), scratch,
-                                    knn_grid_query_bytes(B, Q), st);
+                                    knn_grid_query_bytes(B, Q), st, d.qry_kind == 1 ? W / d.qry_id : 0);
             else
                 rc = knn_brute_launch(sup, qry, B, S, Q, d.K, out[j], idx_is_i64, st);
             if (rc != FFB6D_OK) return rc;

@@ -124,9 +124,11 @@ class KnnGrid:
             check(lib.ffb6d_knn_grid_build(sup.data_ptr(), self.B, self.S, self.k_hint,
                                            self.mem.data_ptr(), self.nbytes, _stream(sup.device)))
 
-    def query(self, query_pts, k, out_dtype=None):
+    def query(self, query_pts, k, out_dtype=None, query_width=0):
         """``query_pts [B,Q,3]`` -> ``[B,Q,k]`` neighbour indices into the support (int32 unless
-        ``out_dtype`` is torch.int64).  Pass the support tensor itself for a self search."""
+        ``out_dtype`` is torch.int64).  Pass the support tensor itself for a self search.
+        ``query_width``: the queries are the pixels of an image with rows of that many points (a
+        performance hint for K = 1, results do not depend on it); 0 = no particular order."""
         _need_cuda(query_pts, "query_pts")
         qry = self.support if query_pts is self.support else query_pts.contiguous().float()
         if qry.dim() != 3 or qry.shape[0] != self.B or qry.shape[2] != 3:
@@ -141,9 +143,10 @@ class KnnGrid:
         with torch.cuda.device(dev):
             sb = int(lib.ffb6d_knn_grid_query_bytes(self.B, Q))
             scratch = torch.empty(max(sb, 1), dtype=torch.uint8, device=dev)
-            check(lib.ffb6d_knn_grid_query(self.support.data_ptr(), qry.data_ptr(), self.B, self.S, Q, k,
-                                           out.data_ptr(), int(dt == torch.int64), self.mem.data_ptr(),
-                                           self.nbytes, scratch.data_ptr(), sb, _stream(dev)))
+            qw = int(query_width) if query_width and Q % int(query_width) == 0 else 0
+            check(lib.ffb6d_knn_grid_query_organized(self.support.data_ptr(), qry.data_ptr(), self.B, self.S, Q, k,
+                                                     out.data_ptr(), int(dt == torch.int64), self.mem.data_ptr(),
+                                                     self.nbytes, scratch.data_ptr(), sb, qw, _stream(dev)))
         return out
 
 
@@ -382,11 +385,13 @@ def fusion_mlp_pack(weight):
     return PackedWeight(weight)
 
 
-def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
+def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None, add=None, add_idx=None,
+               out_channels_last=False):
     """``relu(scale * conv1x1(cat(x1, x2, dim=1)) + shift)`` in one tensor-core kernel
-    (``ffb6d_fusion_mlp_fwd``): the fusion layers of FFB6D (models/ffb6d.py:55-80, 104-129 applied
+    (``ffb6d_fusion_mlp_fwd_ex``): the fusion layers of FFB6D (models/ffb6d.py:55-80, 104-129 applied
     at :246-262, 282-298: ``torch.cat`` -> ``pt_utils.Conv2d(1x1, bias=False)`` -> BatchNorm -> ReLU)
-    with frozen BatchNorm statistics.  Inference only (no backward).
+    with frozen BatchNorm statistics.  Inference (no backward); :mod:`ffb6d_b200.modules` holds the
+    training-mode layers.
 
     :param x1: ``[B, C1, N, 1]`` / ``[B, C1, H, W]`` / ``[B, C1, N]`` float32 CUDA, NCHW-contiguous
     :param x2: second input of the concat with the same trailing shape, or ``None``
@@ -396,7 +401,11 @@ def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
       bias for a layer without BatchNorm
     :param relu: apply ReLU; with ``negative_slope`` given, LeakyReLU(negative_slope) instead (RandLA's
       ``pt_utils.Conv2d``, models/RandLA/pytorch_utils.py:163-197)
-    :return: ``[B, Co, ...]`` with the trailing shape of ``x1``
+    :param add, add_idx: ``add [B, NA, Co]`` (channels-last) and ``add_idx [B, P]`` / ``[B, P, 1]``: the
+      epilogue adds ``add[b, add_idx[b, p], :]`` to the product before the affine (the gathered half of
+      a restructured concat layer, see :func:`ffb6d_b200.fusion.p2r_fuse`)
+    :param out_channels_last: store the result as ``[B, P, Co]`` (what ``add`` of a following call wants)
+    :return: ``[B, Co, ...]`` with the trailing shape of ``x1`` (``[B, P, Co]`` if ``out_channels_last``)
     """
     _need_cuda(x1, "x1")
     if x1.dtype != torch.float32:
@@ -413,27 +422,39 @@ def fusion_mlp(x1, x2, weight, scale, shift, relu=True, negative_slope=None):
             raise ValueError("x2 must be float32 with the batch and trailing shape of x1")
         x2c = x2.contiguous()
         C2 = x2.shape[1]
-    packed = weight if isinstance(weight, PackedWeight) else None
-    if packed is not None:
-        Co, Ci = packed.Co, packed.Ci
-        if packed.device != x1.device:
-            raise ValueError("packed weight lives on %s, inputs on %s" % (packed.device, x1.device))
-    else:
-        w = weight.reshape(weight.shape[0], -1).contiguous().float()
-        Co, Ci = w.shape[0], w.shape[1]
+    packed = weight if isinstance(weight, PackedWeight) else PackedWeight(weight)
+    Co, Ci = packed.Co, packed.Ci
+    if packed.device != x1.device:
+        raise ValueError("packed weight lives on %s, inputs on %s" % (packed.device, x1.device))
     if Ci != C1 + C2:
         raise ValueError("weight has %d input channels, inputs have %d" % (Ci, C1 + C2))
     sc, sh = scale.contiguous().float(), shift.contiguous().float()
     if sc.numel() != Co or sh.numel() != Co:
         raise ValueError("scale/shift must have %d elements" % Co)
-    out = torch.empty((B, Co) + tail, dtype=torch.float32, device=x1.device)
-    fn = lib.ffb6d_fusion_mlp_fwd_packed if packed is not None else lib.ffb6d_fusion_mlp_fwd
-    wptr = packed.data.data_ptr() if packed is not None else w.data_ptr()
+    addc, idxc, i64, NA = None, None, 0, 0
+    if add is not None:
+        _need_cuda(add, "add")
+        if add_idx is None:
+            raise ValueError("add needs add_idx")
+        _need_cuda(add_idx, "add_idx")
+        if add.dtype != torch.float32 or add.dim() != 3 or add.shape[0] != B or add.shape[2] != Co:
+            raise ValueError("add must be float32 [B, NA, Co], got %s" % (tuple(add.shape),))
+        addc = add.contiguous()
+        NA = addc.shape[1]
+        idxc, i64 = _idx_arg(add_idx.reshape(B, -1), "add_idx")
+        if idxc.shape[1] != P:
+            raise ValueError("add_idx must hold one index per position (%d), got %d" % (P, idxc.shape[1]))
+    if out_channels_last:
+        out = torch.empty((B, P, Co), dtype=torch.float32, device=x1.device)
+    else:
+        out = torch.empty((B, Co) + tail, dtype=torch.float32, device=x1.device)
     with torch.cuda.device(x1.device):
-        check(fn(x1c.data_ptr(), C1, x2c.data_ptr() if x2c is not None else None, C2,
-                 wptr, sc.data_ptr(), sh.data_ptr(), B, Co, P,
-                 2 if negative_slope is not None else int(bool(relu)),
-                 float(negative_slope or 0.0), out.data_ptr(), _stream(x1.device)))
+        check(lib.ffb6d_fusion_mlp_fwd_ex(
+            x1c.data_ptr(), C1, x2c.data_ptr() if x2c is not None else None, C2, packed.data.data_ptr(),
+            sc.data_ptr(), sh.data_ptr(), B, Co, P, 2 if negative_slope is not None else int(bool(relu)),
+            float(negative_slope or 0.0), addc.data_ptr() if addc is not None else None,
+            idxc.data_ptr() if idxc is not None else None, i64, NA,
+            LAYOUT_NSC if out_channels_last else LAYOUT_NCS, out.data_ptr(), _stream(x1.device)))
     return out
 
 

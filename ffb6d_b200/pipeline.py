@@ -213,6 +213,68 @@ class FusionMLPs:
         return [ops.fusion_mlp(*a) for a in self.args]
 
 
+class FusionStack:
+    """BASELINE configs[1], "full 4-scale fusion stack": the seven bidirectional fusion stages of
+    ``FFB6D.forward`` (models/ffb6d.py:231-298) chained on this package's kernels -- per stage the set
+    abstraction gather (``random_sample`` / ``nearest_interpolation`` of the point branch), ``p2r_pre`` ->
+    restructured ``p2r_fuse`` (no interpolated map, :mod:`ffb6d_b200.fusion`), the image -> point gather and
+    ``r2p_pre`` -> ``r2p_fuse``; then the final interpolation and the ``choose`` gather (:301-312).
+    The CNN / RandLA layers between the stages are out of scope, so every stage starts from synthetic
+    ``rgb_emb0`` / point features of the reference's widths; inside a stage the data flow is the reference's.
+    Weights are synthetic, BatchNorm folded (inference)."""
+
+    def __init__(self, batch, n_points=12288, h=480, w=640, k=S.K_NEIGH, device="cuda", seed=0):
+        from . import fusion
+        self.B, self.n_points, self.h, self.w, self.k = batch, n_points, h, w, k
+        self.device = torch.device(device)
+        g = torch.Generator(device=self.device).manual_seed(seed)
+
+        def rnd(*shape):
+            return torch.randn(shape, generator=g, device=self.device, dtype=torch.float32)
+
+        def conv(cin, cout):
+            return fusion.FusedConv(rnd(cout, cin) / float(cin) ** 0.5,
+                                    torch.rand(cout, generator=g, device=self.device) + 0.5, rnd(cout) * 0.1)
+
+        N = [S.set_size(("cld", i), n_points) for i in range(5)]
+        self.stages, self.rgb0, self.pts, self.kind = [], [], [], []
+        self.flops = 0
+        dims = [(S.DS_RGB_OC[i], S.DS_RNDLA_OC[i], S.RGB_DS_SR[i], N[i], N[i + 1]) for i in range(S.N_DS_LAYERS)]
+        up_in = (S.DS_RNDLA_OC[3], S.UP_RNDLA_OC[0], S.UP_RNDLA_OC[1])
+        dims += [(S.UP_RGB_OC[i], S.UP_RNDLA_OC[i], S.RGB_UP_SR[i], N[S.N_DS_LAYERS - i], N[S.N_DS_LAYERS - i - 1])
+                 for i in range(S.N_UP_LAYERS)]
+        for j, (cr, cp, sr, n_src, n1) in enumerate(dims):
+            enc = j < S.N_DS_LAYERS
+            self.stages.append(fusion.FusionStage(conv(cr, cp), conv(2 * cp, cp), conv(cp, cr), conv(2 * cr, cr)))
+            self.rgb0.append(rnd(batch, cr, h // sr, w // sr))
+            if enc:      # f_encoder_i on N_i points, pooled to N_{i+1} by random_sample (:240)
+                self.pts.append(rnd(batch, cp, n_src, 1))
+            else:        # decoder: the interpolated point features (:273-275) feed the (out of scope) RandLA
+                         # decoder conv; its output p_emb0 on N_lvl points is synthetic
+                self.pts.append((rnd(batch, up_in[j - S.N_DS_LAYERS], n_src, 1), rnd(batch, cp, n1, 1)))
+            n_pts = n1
+            hw = (h // sr) * (w // sr)
+            self.flops += 2 * batch * (n_pts * (cr * cp + 2 * cp * cp + cp * cr + cr * cr) + hw * cr * cr)
+        self.p_last = rnd(batch, S.UP_RNDLA_OC[2], N[1], 1)       # :302-304
+        self.rgb_last = rnd(batch, S.UP_RGB_OC[2], h, w)          # :309-312
+
+    def __call__(self, inputs, restructured=True):
+        outs = []
+        for i in range(S.N_DS_LAYERS):
+            p_emb0 = ops.random_sample(self.pts[i], inputs["cld_sub_idx%d" % i])
+            outs.append(self.stages[i](self.rgb0[i], p_emb0, inputs["p2r_ds_nei_idx%d" % i],
+                                       inputs["r2p_ds_nei_idx%d" % i], restructured))
+        for i in range(S.N_UP_LAYERS):
+            j, lvl = S.N_DS_LAYERS + i, S.N_DS_LAYERS - i - 1
+            p_prev, p_emb0 = self.pts[j]
+            outs.append(ops.nearest_interpolation(p_prev, inputs["cld_interp_idx%d" % lvl]))
+            outs.append(self.stages[j](self.rgb0[j], p_emb0, inputs["p2r_up_nei_idx%d" % i],
+                                       inputs["r2p_up_nei_idx%d" % i], restructured))
+        outs.append(ops.nearest_interpolation(self.p_last, inputs["cld_interp_idx0"]))
+        outs.append(ops.choose_gather(self.rgb_last, inputs["choose"]))
+        return outs
+
+
 class OpTimer:
     """CUDA-event pair per op on the current stream; durations are read after a synchronize.
     Events come from a pool created up front so that recording costs the CPU as little as possible."""

@@ -134,7 +134,9 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             if (s, kk) in grids:
                 if par:
                     torch.cuda.current_stream(cld.device).wait_event(built[(s, kk)])
-                inputs[key] = grids[(s, kk)].query(qry, kk, out_dtype=index_dtype)
+                # image pyramid levels are organised: rows of W // sr pixels (a layout hint for K = 1)
+                inputs[key] = grids[(s, kk)].query(qry, kk, out_dtype=index_dtype,
+                                                   query_width=(W // q[1]) if q[0] == "img" else 0)
             else:
                 inputs[key] = knn_search(sup, qry, kk, out_dtype=index_dtype, algo=1)
             if timer is not None:

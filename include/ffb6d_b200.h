@@ -111,6 +111,16 @@ int ffb6d_knn_grid_query(const float *support, const float *query,
                          void *idx_out, int idx_is_i64,
                          const void *grid, size_t grid_bytes,
                          void *scratch, size_t scratch_bytes, ffb6d_stream_t stream);
+/* The same search with a layout hint: the Q queries of every batch item are the pixels of an image with
+ * rows of `query_width` points, row after row (the stride pyramids of the organised cloud,
+ * ycb_dataset.py:253-267).  For K = 1 the 32 queries of an 8x4 pixel tile then share one candidate set.
+ * Results are identical to ffb6d_knn_grid_query; query_width = 0 means "no particular order". */
+int ffb6d_knn_grid_query_organized(const float *support, const float *query,
+                                   int64_t B, int64_t S, int64_t Q, int K,
+                                   void *idx_out, int idx_is_i64,
+                                   const void *grid, size_t grid_bytes,
+                                   void *scratch, size_t scratch_bytes,
+                                   int64_t query_width, ffb6d_stream_t stream);
 
 /*
  * The whole index build of a batch in one call: the 22 searches of datasets/ycb/ycb_dataset.py:269-309
@@ -240,6 +250,52 @@ int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const float *x2, in
                                 float *out, ffb6d_stream_t stream);
 
 /*
+ * The packed layer with the two epilogue extras of the restructured fusion stage:
+ *   out = act( scale * ( W * cat(x1, x2) + addend[b, add_idx[b, p], :] ) + shift )
+ * The reference computes rgb' = p2r_fuse(cat(rgb, nearest_interpolation(p2r_pre(p), idx)))
+ * (models/ffb6d.py:246-253, 282-289).  The 1x1 conv is linear and the interpolation a pure selection, so
+ * W * cat(rgb, y[idx]) = W1 * rgb + (W2 * y)[idx]: the small product Z = W2 * y is computed on the N_{i+1}
+ * points (one call with out_layout = FFB6D_LAYOUT_NSC, so that Z is stored [B, NA, Co], a point's channels
+ * contiguous), and the big layer runs over K = C_r only and adds Z[idx[p]] in its epilogue -- the
+ * interpolated map is never materialised and the layer's FLOPs halve.
+ *   addend   [B, NA, Co] f32 channels-last, or NULL;   add_idx [B, P] int32 / int64 (with addend)
+ *   out_layout: FFB6D_LAYOUT_NCS -> out [B, Co, P] (NCHW), FFB6D_LAYOUT_NSC -> out [B, P, Co]
+ */
+int ffb6d_fusion_mlp_fwd_ex(const float *x1, int64_t C1, const float *x2, int64_t C2,
+                            const void *packed, const float *scale, const float *shift,
+                            int64_t B, int64_t Co, int64_t P, int act, float negative_slope,
+                            const float *addend, const void *add_idx, int add_idx_is_i64, int64_t NA,
+                            int out_layout, float *out, ffb6d_stream_t stream);
+
+/* ---- training mode of the 1x1 layers (batch-statistics BatchNorm, backward) ---------------------------
+ * Reference: pt_utils.Conv2d = conv1x1(bias=False) -> BatchNorm2d -> activation, trained with autograd
+ * (models/pytorch_utils.py:75-129; RandLA flavour models/RandLA/pytorch_utils.py:35-111, eps 1e-6,
+ * momentum 0.99; train_ycb.py:464-470 runs backward + Adam over them).  The layer is composed of
+ *   z = W * cat(x1, x2)                 ffb6d_fusion_mlp_fwd_ex (scale 1, shift 0, act 0), z is kept
+ *   y = act(BN_batch(z))                ffb6d_bn_train_fwd   (also updates the running statistics)
+ * and backwards
+ *   dz, dgamma, dbeta from dy           ffb6d_bn_train_bwd
+ *   dW = sum_b dz_b * X_b^T             ffb6d_fusion_mlp_wgrad (tcgen05, split-K, fp32 atomics into dW)
+ *   dX = W^T * dz                       ffb6d_fusion_mlp_fwd_ex with the packed transposed weight
+ * stats [C][4] f32 = (mean, 1/sqrt(var+eps), gamma/sqrt(var+eps), beta) per channel, written by the forward
+ * and read by the backward; workspace: ffb6d_bn_workspace_bytes(C, P) bytes of device memory.
+ * act: 0 none, 1 ReLU, 2 LeakyReLU(negative_slope).  gamma / beta / running_* may be NULL. */
+size_t ffb6d_bn_workspace_bytes(int64_t C, int64_t P);
+int ffb6d_bn_train_fwd(const float *z, int64_t B, int64_t C, int64_t P, const float *gamma, const float *beta,
+                       float eps, float momentum, float *running_mean, float *running_var,
+                       int act, float negative_slope, float *stats, float *y,
+                       void *workspace, size_t workspace_bytes, ffb6d_stream_t stream);
+int ffb6d_bn_train_bwd(const float *z, const float *grad_y, const float *stats, int64_t B, int64_t C, int64_t P,
+                       int act, float negative_slope, float *grad_gamma, float *grad_beta, float *grad_z,
+                       void *workspace, size_t workspace_bytes, ffb6d_stream_t stream);
+/* grad_z = grad_y * act'(z) for a layer with an activation but no BatchNorm. */
+int ffb6d_act_bwd(const float *z, const float *grad_y, int64_t n, int act, float negative_slope, float *grad_z,
+                  ffb6d_stream_t stream);
+/* grad_w [Co, C1+C2] = sum over frames of grad_z [B,Co,P] * cat(x1, x2)^T; grad_w is overwritten. */
+int ffb6d_fusion_mlp_wgrad(const float *grad_z, const float *x1, int64_t C1, const float *x2, int64_t C2,
+                           int64_t B, int64_t Co, int64_t P, float *grad_w, ffb6d_stream_t stream);
+
+/*
  * Attentive pooling core of RandLA's Att_pooling (models/RandLA/RandLANet.py:243-248):
  *   out[b,c,n] = sum_k f[b,c,n,k] * softmax_k(att[b,c,n,:])[k],   f = cat(f1, f2) along channels
  *   f1 [B,C1,N,K], f2 [B,C2,N,K] or NULL, att [B,C1+C2,N,K] -> out [B,C1+C2,N]   (f32, K <= 64)
@@ -247,6 +303,11 @@ int ffb6d_fusion_mlp_fwd_packed(const float *x1, int64_t C1, const float *x2, in
  */
 int ffb6d_att_pool_fwd(const float *f1, int64_t C1, const float *f2, int64_t C2, const float *att,
                        int64_t B, int64_t N, int K, float *out, ffb6d_stream_t stream);
+/* Backward of the above: grad_f[k] = g * s[k], grad_att[k] = s[k] * g * (f[k] - out), s = softmax_k(att).
+ * grad_f1 [B,C1,N,K], grad_f2 [B,C2,N,K] (NULL iff C2 == 0), grad_att [B,C1+C2,N,K]; grad_out [B,C1+C2,N,1]. */
+int ffb6d_att_pool_bwd(const float *f1, int64_t C1, const float *f2, int64_t C2, const float *att,
+                       const float *grad_out, int64_t B, int64_t N, int K,
+                       float *grad_f1, float *grad_f2, float *grad_att, ffb6d_stream_t stream);
 
 /* ---- depth map -> searched point sets ------------------------------------- */
 /*

@@ -240,8 +240,139 @@ def lfa_cases():
     return cases
 
 
+def _ref_pt_utils():
+    """The reference's models/pytorch_utils.py (FFB6D flavour of Conv2d: conv -> BatchNorm2d -> ReLU) as a module."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "ref_ffb6d_pt_utils", os.path.join(R.REF_ROOT, "ffb6d", "models", "pytorch_utils.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def _randomise_bn(module, g):
+    import torch.nn as nn
+    with torch.no_grad():
+        for m in module.modules():
+            if isinstance(m, nn.BatchNorm2d):
+                m.weight.copy_(torch.rand(m.weight.shape, generator=g) + 0.5)
+                m.bias.copy_(torch.randn(m.bias.shape, generator=g) * 0.1)
+                m.running_mean.copy_(torch.randn(m.running_mean.shape, generator=g) * 0.2)
+                m.running_var.copy_(torch.rand(m.running_var.shape, generator=g) + 0.3)
+
+
+def fusion_cases():
+    """One bidirectional fusion stage exactly as FFB6D.forward composes it (models/ffb6d.py:245-263): the four
+    layers are the reference's own pt_utils.Conv2d instances, the gathers its own random_sample /
+    nearest_interpolation (AST-extracted); eval mode, random BatchNorm statistics."""
+    pt = _ref_pt_utils()
+    f = R.torch_functions()
+    cases = {}
+    for name, (B, Cr, Cp, h, w, N1, K, seed) in {"stage_64": (2, 64, 64, 30, 40, 192, 16, 0),
+                                                 "stage_ragged": (1, 40, 24, 9, 11, 50, 16, 1)}.items():
+        torch.manual_seed(seed)
+        g = torch.Generator().manual_seed(50 + seed)
+        layers = {"r2p_pre": pt.Conv2d(Cr, Cp, kernel_size=(1, 1), bn=True),
+                  "r2p_fuse": pt.Conv2d(Cp * 2, Cp, kernel_size=(1, 1), bn=True),
+                  "p2r_pre": pt.Conv2d(Cp, Cr, kernel_size=(1, 1), bn=True),
+                  "p2r_fuse": pt.Conv2d(Cr * 2, Cr, kernel_size=(1, 1), bn=True)}
+        for m in layers.values():
+            _randomise_bn(m, g)
+            m.eval()
+        rgb_emb0 = torch.randn(B, Cr, h, w, generator=g)
+        p_emb0 = torch.randn(B, Cp, N1, 1, generator=g)
+        p2r_idx = torch.randint(0, N1, (B, h * w, 1), generator=g)
+        r2p_idx = torch.randint(0, h * w, (B, N1, K), generator=g)
+        with torch.no_grad():
+            bs, c, hr, wr = rgb_emb0.size()
+            p2r_emb = layers["p2r_pre"](p_emb0)
+            p2r_emb = f["nearest_interpolation"](p2r_emb, p2r_idx)
+            p2r_emb = p2r_emb.view(bs, -1, hr, wr)
+            rgb_emb = layers["p2r_fuse"](torch.cat((rgb_emb0, p2r_emb), dim=1))
+            r2p_emb = f["random_sample"](rgb_emb0.reshape(bs, c, hr * wr, 1), r2p_idx).view(bs, c, -1, 1)
+            r2p_emb = layers["r2p_pre"](r2p_emb)
+            p_emb = layers["r2p_fuse"](torch.cat((p_emb0, r2p_emb), dim=1))
+        cases.update({name + "/rgb_emb0": rgb_emb0.numpy(), name + "/p_emb0": p_emb0.numpy(),
+                      name + "/p2r_idx": p2r_idx.numpy(), name + "/r2p_idx": r2p_idx.numpy(),
+                      name + "/rgb_emb": rgb_emb.numpy(), name + "/p_emb": p_emb.numpy()})
+        for lname, m in layers.items():
+            for k, v in m.state_dict().items():
+                if v.dtype.is_floating_point:
+                    cases["%s/sd.%s.%s" % (name, lname, k)] = v.numpy()
+    return cases
+
+
 def train_cases():
-    return {}
+    """TRAINING-mode fixtures (batch-statistics BatchNorm, autograd gradients) from the reference's own modules:
+    fusion pt_utils.Conv2d layers (models/pytorch_utils.py:75-129) on a concat input, and RandLA's Att_pooling /
+    Dilated_res_block (models/RandLA/RandLANet.py:170-250).  Gradients of a fixed upstream gradient `gout`."""
+    import ast
+    import importlib.util
+    import torch.nn as nn
+    import torch.nn.functional as Fn
+    pt = _ref_pt_utils()
+    cases = {}
+    for name, (B, C1, C2, Co, tail, seed) in {"conv_cat": (2, 24, 40, 48, (12, 10), 0), "conv_pre": (2, 64, 0, 32, (50, 1), 1),
+                                              "conv_wide": (1, 256, 256, 128, (192, 1), 2)}.items():
+        torch.manual_seed(seed)
+        g = torch.Generator().manual_seed(70 + seed)
+        layer = pt.Conv2d(C1 + C2, Co, kernel_size=(1, 1), bn=True)
+        _randomise_bn(layer, g)
+        layer.train()
+        x1 = torch.randn((B, C1) + tail, generator=g).requires_grad_(True)
+        x2 = torch.randn((B, C2) + tail, generator=g).requires_grad_(True) if C2 else None
+        before = {k: v.clone() for k, v in layer.state_dict().items()}
+        x = torch.cat((x1, x2), dim=1) if C2 else x1
+        out = layer(x)
+        gout = torch.randn(out.shape, generator=g)
+        out.backward(gout)
+        cases.update({name + "/x1": x1.detach().numpy(), name + "/out": out.detach().numpy(), name + "/gout": gout.numpy(),
+                      name + "/gx1": x1.grad.numpy(), name + "/gw": layer.conv.weight.grad.numpy(),
+                      name + "/ggamma": layer.normlayer.bn.weight.grad.numpy(),
+                      name + "/gbeta": layer.normlayer.bn.bias.grad.numpy()})
+        if C2:
+            cases.update({name + "/x2": x2.detach().numpy(), name + "/gx2": x2.grad.numpy()})
+        for k, v in before.items():
+            if v.dtype.is_floating_point:
+                cases["%s/sd.%s" % (name, k)] = v.numpy()
+        for k in ("normlayer.bn.running_mean", "normlayer.bn.running_var"):
+            cases["%s/after.%s" % (name, k)] = layer.state_dict()[k].numpy()
+    # RandLA block in training mode
+    rdir = os.path.join(R.REF_ROOT, "ffb6d", "models", "RandLA")
+    spec = importlib.util.spec_from_file_location("ref_randla_pt_utils", os.path.join(rdir, "pytorch_utils.py"))
+    rpt = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(rpt)
+    path = os.path.join(rdir, "RandLANet.py")
+    tree = ast.parse(open(path).read())
+    ns = {"torch": torch, "nn": nn, "F": Fn, "pt_utils": rpt}
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name in ("Dilated_res_block", "Building_block", "Att_pooling"):
+            exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+    for name, (d_in, d_out, B, N, K, seed) in {"blk_train_8_16": (8, 16, 2, 96, 16, 0),
+                                               "blk_train_64_64": (64, 64, 1, 192, 16, 1)}.items():
+        torch.manual_seed(seed)
+        blk = ns["Dilated_res_block"](d_in, d_out)
+        g = torch.Generator().manual_seed(200 + seed)
+        _randomise_bn(blk, g)
+        blk.train()
+        feature = torch.randn(B, d_in, N, 1, generator=g).requires_grad_(True)
+        xyz = torch.randn(B, N, 3, generator=g)
+        idx = torch.randint(0, N, (B, N, K), generator=g)
+        before = {k: v.clone() for k, v in blk.state_dict().items()}
+        out = blk(feature, xyz, idx)
+        gout = torch.randn(out.shape, generator=g)
+        out.backward(gout)
+        cases.update({name + "/feature": feature.detach().numpy(), name + "/xyz": xyz.numpy(), name + "/idx": idx.numpy(),
+                      name + "/out": out.detach().numpy(), name + "/gout": gout.numpy(), name + "/gfeature": feature.grad.numpy()})
+        for k, v in before.items():
+            if v.dtype.is_floating_point:
+                cases["%s/sd.%s" % (name, k)] = v.numpy()
+        for k, prm in blk.named_parameters():
+            cases["%s/grad.%s" % (name, k)] = prm.grad.numpy()
+        for k, v in blk.state_dict().items():
+            if "running_" in k:
+                cases["%s/after.%s" % (name, k)] = v.numpy()
+    return cases
 
 
 def main():
@@ -250,7 +381,8 @@ def main():
     R.build_ref()
     if len(sys.argv) > 2 and sys.argv[1] == "--only":      # regenerate one fixture file
         which = sys.argv[2]
-        fn = {"lfa": lfa_cases, "knn": knn_cases, "gather": gather_cases, "grid": grid_cases, "train": train_cases}[which]
+        fn = {"lfa": lfa_cases, "knn": knn_cases, "gather": gather_cases, "grid": grid_cases, "train": train_cases,
+              "fusion": fusion_cases}[which]
         np.savez_compressed(os.path.join(OUT, which + "_cases.npz"), **fn())
         print("rewrote", which + "_cases.npz")
         return
@@ -258,6 +390,8 @@ def main():
     np.savez_compressed(os.path.join(OUT, "gather_cases.npz"), **gather_cases())
     np.savez_compressed(os.path.join(OUT, "grid_cases.npz"), **grid_cases())
     np.savez_compressed(os.path.join(OUT, "lfa_cases.npz"), **lfa_cases())
+    np.savez_compressed(os.path.join(OUT, "fusion_cases.npz"), **fusion_cases())
+    np.savez_compressed(os.path.join(OUT, "train_cases.npz"), **train_cases())
     dig = {"generator": "ffb6d_b200.synthetic.make_frame", "frames": {}}
     for seed, n in ((0, 12288), (1, 12288), (2, 3072)):
         dig["frames"]["seed%d_n%d" % (seed, n)] = {"seed": seed, "n_points": n,

@@ -235,6 +235,38 @@ def test_stress_sweep_sizes(cuda, n_points, k):
             assert (idx[:, 0] == np.arange(Q)).all(), key
 
 
+def test_knn_organised_queries_tile_path(cuda):
+    """K = 1 with the `query_width` layout hint (one warp per 8x4 pixel tile sharing a candidate box) gives
+    exactly the result of the plain search: image shapes that do not divide into tiles, hole pixels at the
+    origin (+0.0 / -0.0), a depth discontinuity (box too large -> per-thread finish), NaN queries."""
+    from ffb6d_b200.synthetic import make_frame, image_pyramid_np
+    fr = make_frame(9, n_points=3072)
+    pyr = image_pyramid_np(fr["dpt_xyz"])
+    rs = np.random.RandomState(5)
+    cases = []
+    for sr, (hh, ww) in ((8, (60, 80)), (4, (120, 160))):
+        q = pyr[sr].reshape(hh, ww, 3).copy()
+        cases.append((q, ww))
+        cut = q[: hh - 3, : ww - 6].copy()                      # 57 x 74 / 117 x 154: ragged tiles
+        cut[5:9, 10:30, 2] += 0.6                                # a step in depth inside tiles
+        cut[20, 20] = np.nan
+        cut[21, 21:25] = -0.0
+        cases.append((cut, ww - 6))
+    sup = np.stack([fr["cld"][:3072], fr["cld"][:3072] * np.array([1.0, 1.0, 1.1], np.float32)])
+    grid = F.KnnGrid(torch.from_numpy(sup).cuda(), 1)
+    for img, ww in cases:
+        q = np.stack([img.reshape(-1, 3), img[::-1].reshape(-1, 3)]).astype(np.float32)
+        tq = torch.from_numpy(q).cuda()
+        plain = grid.query(tq, 1).cpu().numpy()
+        tiled = grid.query(tq, 1, query_width=ww).cpu().numpy()
+        assert np.array_equal(plain, tiled), (img.shape, ww)
+        ok = ~np.isnan(q).any(axis=2)
+        want = O.knn_search(sup, np.nan_to_num(q), 1)
+        assert np.array_equal(tiled[ok], want[ok])
+        for dt in (torch.int64,):
+            assert np.array_equal(grid.query(tq, 1, out_dtype=dt, query_width=ww).cpu().numpy(), tiled)
+
+
 @pytest.mark.parametrize("k", [2, 31, 32, 33, 64])
 def test_knn_all_k_paths(cuda, k):
     """warp-per-query (K <= 32) and thread-per-query (K > 32) searches, overflow paths included."""
