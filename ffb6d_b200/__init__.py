@@ -24,11 +24,11 @@ import importlib
 
 _OPS = ("knn_search", "random_sample", "nearest_interpolation", "gather_neighbour", "relative_pos_encoding",
         "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack",
-        "PackedWeight", "fold_batchnorm", "att_pool")
+        "PackedWeight", "fold_batchnorm", "att_pool", "sample_valid_pixels", "check_indices")
 _SCHEDULE = ("build_ffb6d_indices", "build_ffb6d_indices_from_depth", "build_ffb6d_indices_native")
 _TABLES = ("knn_schedule", "gather_schedule", "fusion_mlp_schedule")
 _SUBMODULES = ("ops", "schedule", "tables", "synthetic", "pipeline", "randla", "modules", "fusion", "dist",
-               "helper_tool", "_lib")
+               "helper_tool", "model", "_lib")
 
 __all__ = list(_OPS + _SCHEDULE + _TABLES) + ["randla", "modules", "fusion", "DataProcessing"]
 

@@ -140,9 +140,9 @@ class _ConvBnActTrain(torch.autograd.Function):
 class _BNWrap(nn.Sequential):
     """The reference's ``_BNBase``: a Sequential holding one BatchNorm2d named ``bn``."""
 
-    def __init__(self, channels, eps, momentum):
+    def __init__(self, channels, eps, momentum, dims=2):
         super().__init__()
-        self.add_module("bn", nn.BatchNorm2d(channels, eps=eps, momentum=momentum))
+        self.add_module("bn", (nn.BatchNorm2d if dims == 2 else nn.BatchNorm1d)(channels, eps=eps, momentum=momentum))
         nn.init.constant_(self[0].weight, 1.0)
         nn.init.constant_(self[0].bias, 0)
 
@@ -151,13 +151,18 @@ class _ConvBase(nn.Module):
     _bn_name = "normlayer"
     _bn_eps, _bn_momentum = 1e-5, 0.1
 
+    _dims = 2
+
     def __init__(self, in_size, out_size, kernel_size=(1, 1), activation=None, bn=False, init=nn.init.kaiming_normal_,
                  bias=True, name=""):
         super().__init__()
-        if tuple(kernel_size) != (1, 1):
+        ks = (kernel_size,) if isinstance(kernel_size, int) else tuple(kernel_size)
+        if any(k != 1 for k in ks):
             raise ValueError("only the 1x1 layers of the fusion / RandLA path are implemented here")
         bias = bias and (not bn)
-        conv_unit = nn.Conv2d(in_size, out_size, kernel_size=(1, 1), bias=bias)    # holds the parameters
+        # holds the parameters under the reference's names; the arithmetic runs in the CUDA library
+        conv_unit = (nn.Conv2d(in_size, out_size, kernel_size=(1, 1), bias=bias) if self._dims == 2
+                     else nn.Conv1d(in_size, out_size, kernel_size=1, bias=bias))
         init(conv_unit.weight)
         if bias:
             nn.init.constant_(conv_unit.bias, 0)
@@ -165,7 +170,7 @@ class _ConvBase(nn.Module):
         self.add_module(name + "conv", conv_unit)
         self.has_bn = bool(bn)
         if bn:
-            self.add_module(name + self._bn_name, _BNWrap(out_size, self._bn_eps, self._bn_momentum))
+            self.add_module(name + self._bn_name, _BNWrap(out_size, self._bn_eps, self._bn_momentum, self._dims))
         if activation is not None:
             self.add_module(name + "activation", activation)
         self.act, self.slope = _act_code(activation)
@@ -194,6 +199,11 @@ class _ConvBase(nn.Module):
         return self._packed[1:]
 
     def forward(self, x, x2=None):
+        if self._dims == 1:     # [B, C, N] layers run as [B, C, N, 1]
+            return self._forward(x.unsqueeze(3), x2.unsqueeze(3) if x2 is not None else None).squeeze(3)
+        return self._forward(x, x2)
+
+    def _forward(self, x, x2=None):
         conv, bn = self._conv, self._bn
         need_grad = torch.is_grad_enabled() and (x.requires_grad or conv.weight.requires_grad or
                                                  (x2 is not None and x2.requires_grad))
@@ -240,6 +250,32 @@ class RandLAConv2d(_ConvBase):
                  bias=True, preact=False, name="", instance_norm=False):
         if preact or instance_norm or tuple(stride) != (1, 1) or tuple(padding) != (0, 0):
             raise ValueError("only plain 1x1 layers are implemented here")
+        super().__init__(in_size, out_size, kernel_size, activation, bn, init, bias, name)
+
+
+class Conv1d(_ConvBase):
+    """``pt_utils.Conv1d`` of FFB6D's prediction heads (models/pytorch_utils.py:132-165), kernel size 1: input
+    ``[B, C, N]``.  State-dict keys as :class:`Conv2d` (``conv.weight`` is ``[Co, Ci, 1]``)."""
+    _dims = 1
+
+    def __init__(self, in_size, out_size, kernel_size=1, stride=1, padding=0, dilation=1,
+                 activation=nn.ReLU(inplace=True), bn=False, init=nn.init.kaiming_normal_, bias=True, preact=False, name=""):
+        if preact or stride != 1 or padding != 0 or dilation != 1:
+            raise ValueError("only plain kernel-size-1 layers are implemented here")
+        super().__init__(in_size, out_size, kernel_size, activation, bn, init, bias, name)
+
+
+class RandLAConv1d(_ConvBase):
+    """RandLA's ``pt_utils.Conv1d`` (``fc0`` of the network, models/RandLA/RandLANet.py:16), kernel size 1."""
+    _dims = 1
+    _bn_name = "bn"
+    _bn_eps, _bn_momentum = 1e-6, 0.99
+
+    def __init__(self, in_size, out_size, *, kernel_size=1, stride=1, padding=0,
+                 activation=nn.LeakyReLU(negative_slope=0.2, inplace=True), bn=False, init=nn.init.kaiming_normal_,
+                 bias=True, preact=False, name="", instance_norm=False):
+        if preact or instance_norm or stride != 1 or padding != 0:
+            raise ValueError("only plain kernel-size-1 layers are implemented here")
         super().__init__(in_size, out_size, kernel_size, activation, bn, init, bias, name)
 
 

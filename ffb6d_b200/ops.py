@@ -519,6 +519,32 @@ def backproject(depth, K, choose):
     return _backproject(depth, torch.from_numpy(intr).to(dev), per_frame, choose)
 
 
+def sample_valid_pixels(depth, n_points, seed=0, min_depth=1e-8, return_count=False):
+    """The datasets' point sampling on the GPU (datasets/ycb/ycb_dataset.py:218-235): the valid pixels of each
+    depth map (``depth > min_depth``) are compacted, ``n_points`` of them are drawn uniformly without replacement
+    (all of them, repeated cyclically like ``np.pad(..., 'wrap')``, when fewer exist) and returned in uniformly
+    random order.  Deterministic per ``seed``; the picks have the reference's distribution but do not replay
+    numpy's random stream.
+
+    :param depth: ``[B,H,W]`` float32 CUDA; :return: ``choose [B,1,n_points]`` int32 flat pixel indices
+      (what :func:`backproject` and the final ``choose`` gather take); with ``return_count`` also the number
+      of valid pixels per frame ``[B]`` int32."""
+    _need_cuda(depth, "depth")
+    if depth.dim() != 3 or depth.dtype != torch.float32:
+        raise ValueError("depth must be float32 [B,H,W]")
+    depth = depth.contiguous()
+    B, H, W = depth.shape
+    dev = depth.device
+    choose = torch.empty((B, 1, int(n_points)), dtype=torch.int32, device=dev)
+    count = torch.empty((B,), dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        nbytes = int(lib.ffb6d_sample_pixels_workspace_bytes(B, H, W))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        check(lib.ffb6d_sample_pixels(depth.data_ptr(), B, H, W, float(min_depth), int(n_points), int(seed) & (2 ** 64 - 1),
+                                      choose.data_ptr(), count.data_ptr(), ws.data_ptr(), nbytes, _stream(dev)))
+    return (choose, count) if return_count else choose
+
+
 def intrinsics_to_device(K, device, batch=None):
     """Camera matrix ``[3,3]`` / ``[B,3,3]`` -> float64 ``[4]`` / ``[B,4]`` (fx, fy, cx, cy) on the device."""
     Kn = np.asarray(K, dtype=np.float64)

@@ -29,11 +29,15 @@ class FusionPass:
         self.device = torch.device(device)
         self.layout = layout
         self.index_dtype = index_dtype
-        self.streams = [torch.cuda.Stream(device=self.device) for _ in range(n_streams)] if n_streams > 1 else None
+        import os
+        # FFB6D_STREAM_PRIO="s,g": CUDA priorities of the search / gather streams (experiment switch; lower = higher)
+        prio = [int(x) for x in os.environ.get("FFB6D_STREAM_PRIO", "0,0").split(",")]
+        self.streams = ([torch.cuda.Stream(device=self.device, priority=prio[0]) for _ in range(n_streams)]
+                        if n_streams > 1 else None)
         # the gathers (HBM bound) get streams of their own: each waits only for its index tensor, so
         # it overlaps the searches (issue bound) that are still running
-        self.gstreams = ([torch.cuda.Stream(device=self.device) for _ in range(n_gather_streams or n_streams)]
-                         if n_streams > 1 else None)
+        self.gstreams = ([torch.cuda.Stream(device=self.device, priority=prio[1])
+                          for _ in range(n_gather_streams or n_streams)] if n_streams > 1 else None)
         self.gathers = S.gather_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.features = []

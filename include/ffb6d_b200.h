@@ -324,6 +324,20 @@ int ffb6d_backproject(const float *depth, int64_t B, int64_t H, int64_t W,
                       const int *choose, int64_t N,
                       float *cld, float *pyr2, float *pyr4, float *pyr8, ffb6d_stream_t stream);
 
+/*
+ * Valid-pixel compaction + seeded point sampling on the device: replaces the reference's CPU recipe
+ * (datasets/ycb/ycb_dataset.py:218-235: `nonzero()` of the depth mask, a random subset of N valid pixels --
+ * or all of them repeated cyclically ('wrap') when fewer exist --, then a random permutation).
+ *   depth [B,H,W] f32 (valid where > min_depth) -> choose [B,N] int32 flat pixel indices, the `choose`
+ *   input of ffb6d_backproject; valid_count [B] int32 (device, may be NULL) = number of valid pixels.
+ * Deterministic per (seed, frame index).  Same distribution as the reference (uniform subset, uniform order);
+ * numpy's own random stream is not reproduced.  workspace: ffb6d_sample_pixels_workspace_bytes(B,H,W) bytes.
+ */
+size_t ffb6d_sample_pixels_workspace_bytes(int64_t B, int64_t H, int64_t W);
+int ffb6d_sample_pixels(const float *depth, int64_t B, int64_t H, int64_t W, float min_depth, int64_t N,
+                        uint64_t seed, int *choose, int *valid_count, void *workspace, size_t workspace_bytes,
+                        ffb6d_stream_t stream);
+
 /* ---- grid subsampling --------------------------------------------------- */
 /*
  * Voxel-grid barycentre subsampling, replaces grid_subsampling()
