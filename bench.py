@@ -293,6 +293,7 @@ def main():
     ap.add_argument("--gather-streams", type=int, default=0, help="side streams of the gathers (0: same number)")
     ap.add_argument("--no-graph", action="store_true", help="time eager launches instead of CUDA graph replays")
     ap.add_argument("--per-op", action="store_true", help="also print the per-op table to stderr")
+    ap.add_argument("--l2-fetch", type=int, default=0, help="experiment: cudaLimitMaxL2FetchGranularity (32/64/128 bytes)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -322,6 +323,14 @@ def main():
                          "(use --impl reference for the CPU arm)")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    if args.l2_fetch:
+        import ctypes
+        torch.zeros(1, device=dev)                      # context
+        rt = ctypes.CDLL("libcudart.so.12")
+        rc_ = rt.cudaDeviceSetLimit(5, ctypes.c_size_t(args.l2_fetch))       # cudaLimitMaxL2FetchGranularity
+        got_ = ctypes.c_size_t(0)
+        rt.cudaDeviceGetLimit(ctypes.byref(got_), 5)
+        sys.stderr.write("bench.py: L2 fetch granularity -> %d (rc %d)\n" % (got_.value, rc_))
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -639,6 +648,51 @@ def main():
         except Exception as e:                      # noqa: BLE001
             stack_line = {"error": str(e)[:300]}
 
+    # ---- RandLA local feature aggregation: the four encoder Dilated_res_blocks of the
+    # point branch at FFB6D's widths, inference, on the index tensors of this pass; reported against the
+    # survey's LFA gather byte model (56.6 MB/frame at N0 = 12288, K = 16: the three neighbour gathers per block)
+    lfa_line = None
+    if not args.no_mlp:
+        try:
+            from ffb6d_b200 import modules as M_
+            blocks, feats_ = [], []
+            d_in = 8
+            gl = torch.Generator(device=dev).manual_seed(rank)
+            for i_, d_ in enumerate((32, 64, 128, 256)):
+                blk = M_.Dilated_res_block(d_in, d_).to(dev).eval()
+                blocks.append(blk)
+                feats_.append(torch.randn((B, d_in, N0 // 4 ** i_, 1), generator=gl, device=dev))
+                d_in = 2 * d_
+            idx_in = resident_res[0]
+
+            def lfa():
+                with torch.no_grad():
+                    return [blk(f_, idx_in["cld_xyz%d" % i_], idx_in["cld_nei_idx%d" % i_])
+                            for i_, (blk, f_) in enumerate(zip(blocks, feats_))]
+
+            for _ in range(2):
+                lfa()
+            torch.cuda.synchronize()
+            t0_, t1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            reps = 5
+            t0_.record()
+            for _ in range(reps):
+                lfa()
+            t1_.record()
+            torch.cuda.synchronize()
+            lfa_ms = t0_.elapsed_time(t1_) / reps
+            lfa_bytes = sum(4 * (N0 // 4 ** i_) * args.k * (3 + 2 * d_ // 2) for i_, d_ in enumerate((32, 64, 128, 256)))
+            lfa_line = {"what": "4 encoder Dilated_res_blocks (relative position encoding, 2 neighbour gathers, 2 attentive "
+                                "poolings, 6 conv+BN layers each) on this package's kernels, inference, eager launches",
+                        "ms_per_step": lfa_ms, "gather_alg_bytes_per_frame": lfa_bytes,
+                        "gather_model_GBps": lfa_bytes * B / (lfa_ms / 1e3) / 1e9,
+                        "note": "per-op kernels: the [B,C,N,K] neighbour / attention tensors still pass through HBM "
+                                "(a fused gather -> fc -> softmax-pool -> mlp kernel is the open row f-2)"}
+            del blocks, feats_
+            torch.cuda.empty_cache()
+        except Exception as e:                      # noqa: BLE001
+            lfa_line = {"error": str(e)[:300]}
+
     # ---- comparators on the same box.  C5: the reference's own torch expressions
     # (models/ffb6d.py:159-194, restated in _torch_cpu_random_sample) on THIS GPU with the same features and
     # int64 indices (train_ycb.py:224-232 casts them before the forward pass; the cast is not timed).
@@ -738,7 +792,7 @@ def main():
                              "enqueue a step" % (spin_ms / steps, enqueue_ms / steps),
         "digest_ok": digest_ok, "reference_digest_ok": reference_digest_ok,
         "roofline": roofline, "compute": compute, "pass_roofline": pass_roofline,
-        "fusion_mlps": mlp_line, "fusion_stack": stack_line, "cpu_baseline": cpu_baseline, "gpu_torch_reference": gpu_torch,
+        "fusion_mlps": mlp_line, "fusion_stack": stack_line, "lfa_blocks": lfa_line, "cpu_baseline": cpu_baseline, "gpu_torch_reference": gpu_torch,
         "host_api": host_api, "clocks": clocks,
     }
     emit(line)
