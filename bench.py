@@ -260,20 +260,25 @@ def load_ncu_traffic():
         return {}
 
 
+K1_FAMILY = "K=1 searches (grid_search_k1_tile_kernel for image queries, grid_search_kernel<1>, knn_brute for S<512)"
+SELF_FAMILY = "grid_search_group_kernel<SELF> (K=16 self searches)"
+NONSELF_FAMILY = "grid_search_group_kernel<non-self> (K=16 cloud -> image searches)"
+BUILD_FAMILY = "grid_build_kernel (one cluster launch per grid)"
+
+
 def kernel_family(op_name):
     """Map a timed op to the kernel (family) that runs it.  Gathers are single kernels and are
-    grouped by kernel function; a KNN search op is grid_search_* + overflow + dup-copy (the search
-    kernel is > 90 % of it), a KNN build op is the five grid-build kernels."""
+    grouped by kernel function; a KNN search op is its search kernel + overflow pass (the search
+    kernel is > 90 % of it), a KNN build op is one grid_build_kernel launch."""
     parts = op_name.split(":")
     kind, key = parts[0], parts[1]
     if kind == "gather":
         return parts[2]
     if kind == "knn_build":
-        return "grid build (prepare+zero+count+scan+scatter)"
+        return BUILD_FAMILY
     if "interp" in key or key.startswith("p2r"):
-        return "grid_search_kernel<K=1> (+knn_brute for S<512)"
-    # the self searches (cld_nei_idx*) and the r2p searches run different instantiations
-    return "grid_search_warp_kernel<SELF>" if key.startswith("cld_nei") else "grid_search_warp_kernel<non-self>"
+        return K1_FAMILY
+    return SELF_FAMILY if key.startswith("cld_nei") else NONSELF_FAMILY
 
 
 def main():
@@ -550,12 +555,13 @@ def main():
         if k.startswith("gather"):
             continue
         entry = {"share": v["ms"] / tot_ms, "ms_per_step": v["ms"] / steps}
-        if "K=1" in k:
+        if k == K1_FAMILY:
             entry["queries_per_step"] = n_q["k1"]
-        elif "SELF" in k:
+        elif k == SELF_FAMILY:
             entry["queries_per_step"] = n_q["k16_self"]
-        elif "non-self" in k:
+        elif k == NONSELF_FAMILY:
             entry["queries_per_step"] = n_q["k16"]
+            entry["note"] = "4 of the 7 searches are row slices of the other 3 (cloud levels are prefixes): not run"
         if "queries_per_step" in entry and v["ms"] > 0:
             entry["ns_per_query"] = v["ms"] / steps * 1e6 / entry["queries_per_step"]
         cap_k = ncu.get(k)

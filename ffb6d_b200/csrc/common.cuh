@@ -71,12 +71,18 @@ static inline int num_sms() { return device_info().num_sms; }
         }                                                                                          \
     } while (0)
 
+// train.cu: weight gradient of narrow layers (used by ffb6d_fusion_mlp_wgrad, fusion_mlp.cu)
+int wgrad_small_launch(const float *grad_z, const float *x1, int64_t C1, const float *x2, int64_t C2, int64_t B, int64_t Co,
+                       int64_t P, float *grad_w, cudaStream_t st);
+
 // Experiment switches, read ONCE per process (never in a launch path; results never depend on them).
 struct Env {
     bool gather_direct;     // FFB6D_GATHER_DIRECT=1: K-lane gathers through the older direct kernel
     bool mlp_no_direct;     // FFB6D_MLP_NO_DIRECT=1
     bool check_indices;     // FFB6D_CHECK_INDICES=1: validate gather indices (synchronises; debugging aid)
     bool grid_thread_search;
+    int knn_max_ctas;       // FFB6D_KNN_MAX_CTAS=n: cap the search kernels at n CTAs per SM (leaves registers and warp
+                            // slots to the HBM-bound gathers that run concurrently); 0 = no cap
     float grid_scale, grid_scale_k1;
     int grid_quantile;
 };

@@ -748,6 +748,8 @@ extern "C" int ffb6d_fusion_mlp_wgrad(const float *grad_z, const float *x1, int6
     FFB6D_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)Co * Ci * sizeof(float), st));
     if (B == 0 || P == 0) return FFB6D_OK;
     FFB6D_CHECK_ARG(grad_z && x1 && (C2 == 0 || x2), "fusion_mlp_wgrad: null pointer");
+    if (Co <= 64 && Ci <= 64)   // narrow layer: a 128x128 tensor-core tile would be mostly padding (train.cu)
+        return wgrad_small_launch(grad_z, x1, C1, x2, C2, B, Co, P, grad_w, st);
     FFB6D_OPTIN_SMEM(fusion_wgrad_kernel, WG_SMEM);
     const int64_t tpf = ceil_div(P, TK), total = B * tpf;
     FFB6D_CHECK_ARG(total < (1ll << 31), "fusion_mlp_wgrad: B * P too large");

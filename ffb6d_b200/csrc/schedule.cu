@@ -133,6 +133,19 @@ extern "C" int ffb6d_build_indices(const float *cld, const float *img2, const fl
     Call calls[22];
     make_calls(K, calls);
     bool done[22] = {};
+    // Cloud level j is a row prefix of level i < j: a search of the same support with the same K whose queries are a
+    // deeper cloud level is a row slice of the shallower one (r2p_ds_nei_idx2/3 of idx1, r2p_up_nei_idx0 of
+    // r2p_ds_nei_idx0, r2p_up_nei_idx1 of idx2): those four are copied, not searched.
+    int parent[22];
+    for (int i = 0; i < 22; ++i) {
+        parent[i] = -1;
+        if (calls[i].qry_kind != 0) continue;
+        for (int j = 0; j < 22; ++j)
+            if (j != i && calls[j].qry_kind == 0 && calls[j].sup_kind == calls[i].sup_kind && calls[j].sup_id == calls[i].sup_id &&
+                calls[j].K == calls[i].K && calls[j].qry_id < calls[i].qry_id &&
+                (parent[i] < 0 || calls[j].qry_id < calls[parent[i]].qry_id))
+                parent[i] = j;
+    }
     void *grid = ws + plan.grid_off, *scratch = ws + plan.scratch_off;
     for (int i = 0; i < 22; ++i) {
         if (done[i]) continue;
@@ -151,6 +164,7 @@ extern "C" int ffb6d_build_indices(const float *cld, const float *img2, const fl
         for (int j = i; j < 22; ++j) {
             const Call &d = calls[j];
             if (done[j] || d.sup_kind != c.sup_kind || d.sup_id != c.sup_id || d.K != c.K) continue;
+            if (parent[j] >= 0) continue;   // a row slice of another search: copied below
             const int64_t Q = size_of(z, d.qry_kind, d.qry_id);
             const float *qry = set_ptr(d.qry_kind, d.qry_id);
             int rc;
@@ -162,6 +176,14 @@ extern "C" int ffb6d_build_indices(const float *cld, const float *img2, const fl
             if (rc != FFB6D_OK) return rc;
             done[j] = true;
         }
+    }
+    const size_t esz = idx_is_i64 ? 8 : 4;
+    for (int i = 0; i < 22; ++i) {
+        if (parent[i] < 0) continue;
+        const int64_t Qc = size_of(z, calls[i].qry_kind, calls[i].qry_id), Qp = size_of(z, calls[parent[i]].qry_kind, calls[parent[i]].qry_id);
+        const size_t row = (size_t)calls[i].K * esz;
+        FFB6D_CUDA(cudaMemcpy2DAsync(out[i], (size_t)Qc * row, out[parent[i]], (size_t)Qp * row, (size_t)Qc * row, (size_t)B,
+                                     cudaMemcpyDeviceToDevice, st));
     }
     return FFB6D_OK;
 }

@@ -205,7 +205,9 @@ act_bwd_kernel(const float *__restrict__ z, const float *__restrict__ g, long lo
 
 // ------------------------------------------------------------------ attentive pooling backward
 // forward: out[b,c,n] = sum_k f[k] * s[k], s = softmax_k(att)   (models/RandLA/RandLANet.py:245-248)
-// backward: df[k] = g * s[k];  datt[k] = s[k] * g * (f[k] - out)
+// backward: df[k] = g * s[k];  datt[k] = s[k] * g * (f[k] - out).  One thread per (b, c, n); with KT = 16 the
+// thread's 64-byte rows of f / att / df / datt move as four 128-bit accesses each and exp is evaluated once.
+template <int KT>
 __global__ void __launch_bounds__(256)
 att_pool_bwd_kernel(const float *__restrict__ f1, int C1, const float *__restrict__ f2, int C2, const float *__restrict__ att,
                     const float *__restrict__ gout, int N, int K, float *__restrict__ gf1, float *__restrict__ gf2,
@@ -223,17 +225,113 @@ att_pool_bwd_kernel(const float *__restrict__ f1, int C1, const float *__restric
     const float *ap = att + (size_t)t * K;
     float *gap = gatt + (size_t)t * K;
     const float g = __ldg(gout + t);
-    float m = __ldg(ap);
-    for (int k = 1; k < K; ++k) m = fmaxf(m, __ldg(ap + k));
-    float den = 0.f;
-    for (int k = 0; k < K; ++k) den += expf(__ldg(ap + k) - m);
-    float out = 0.f;
-    for (int k = 0; k < K; ++k) out += __ldg(fp + k) * (expf(__ldg(ap + k) - m) / den);
-    for (int k = 0; k < K; ++k) {
-        const float s = expf(__ldg(ap + k) - m) / den;
-        gfp[k] = g * s;
-        gap[k] = s * g * (__ldg(fp + k) - out);
+    if constexpr (KT > 0) {
+        float fv[KT], av[KT];
+#pragma unroll
+        for (int q = 0; q < KT / 4; ++q) {
+            const float4 u = __ldg(reinterpret_cast<const float4 *>(fp) + q), v = __ldg(reinterpret_cast<const float4 *>(ap) + q);
+            fv[4 * q] = u.x; fv[4 * q + 1] = u.y; fv[4 * q + 2] = u.z; fv[4 * q + 3] = u.w;
+            av[4 * q] = v.x; av[4 * q + 1] = v.y; av[4 * q + 2] = v.z; av[4 * q + 3] = v.w;
+        }
+        float m = av[0];
+#pragma unroll
+        for (int k = 1; k < KT; ++k) m = fmaxf(m, av[k]);
+        float den = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            av[k] = expf(av[k] - m);
+            den += av[k];
+        }
+        float out = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k) {
+            av[k] = av[k] / den;
+            out += fv[k] * av[k];
+        }
+#pragma unroll
+        for (int q = 0; q < KT / 4; ++q) {
+            float4 a, d;
+            a.x = g * av[4 * q]; a.y = g * av[4 * q + 1]; a.z = g * av[4 * q + 2]; a.w = g * av[4 * q + 3];
+            d.x = a.x * (fv[4 * q] - out); d.y = a.y * (fv[4 * q + 1] - out);
+            d.z = a.z * (fv[4 * q + 2] - out); d.w = a.w * (fv[4 * q + 3] - out);
+            reinterpret_cast<float4 *>(gfp)[q] = a;
+            reinterpret_cast<float4 *>(gap)[q] = d;
+        }
+    } else {
+        float m = __ldg(ap);
+        for (int k = 1; k < K; ++k) m = fmaxf(m, __ldg(ap + k));
+        float den = 0.f;
+        for (int k = 0; k < K; ++k) den += expf(__ldg(ap + k) - m);
+        float out = 0.f;
+        for (int k = 0; k < K; ++k) out += __ldg(fp + k) * (expf(__ldg(ap + k) - m) / den);
+        for (int k = 0; k < K; ++k) {
+            const float s = expf(__ldg(ap + k) - m) / den;
+            gfp[k] = g * s;
+            gap[k] = s * g * (__ldg(fp + k) - out);
+        }
     }
+}
+
+// ------------------------------------------------------------------ weight gradient of NARROW layers
+// dW[co, ci] = sum_{b,p} dz[b, co, p] * x[b, ci, p] for Co, Ci <= 64 (the RandLA layers on [B, C, N, K] tensors:
+// 10 -> 16 ... 64 -> 64 channels over millions of positions).  A 128 x 128 tensor-core tile would be > 90 % padding
+// there and the k-loop latency bound; this is a streaming reduction instead: a CTA takes a run of positions, stages
+// 64-position slabs of dz and x in shared memory (coalesced along p) and every thread accumulates a 4 x 4 block of
+// dW in registers (fp32 FMA); CTA partials are added to dW with atomics.
+constexpr int WS_TP = 64;    // positions per slab
+// T = tile edge (16, 32, 64: the smallest that holds Co and Ci); a thread owns a (T/16) x (T/16) block of dW and
+// walks the slab four positions at a time with 128-bit shared-memory loads.
+template <int T>
+__global__ void __launch_bounds__(256)
+wgrad_small_kernel(const float *__restrict__ dz, const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
+                   float *__restrict__ dw, int Co, int P, int B, int slabs_per_cta)
+{
+    constexpr int R = T / 16;                    // rows of dz / x per thread
+    constexpr int LD = WS_TP + 4;                // row stride: 16-byte aligned rows, conflict-free 128-bit loads
+    __shared__ __align__(16) float sz[T * LD], sx[T * LD];
+    const int Ci = C1 + C2;
+    const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;     // dW rows R*ty .., columns R*tx ..
+    float acc[R][R];
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
+    const long long slabs_per_frame = (P + WS_TP - 1) / WS_TP, total = slabs_per_frame * B;
+    const long long s0 = (long long)blockIdx.x * slabs_per_cta, s1 = min(total, s0 + slabs_per_cta);
+    for (long long sl = s0; sl < s1; ++sl) {
+        const int b = (int)(sl / slabs_per_frame), p0 = (int)(sl % slabs_per_frame) * WS_TP;
+        __syncthreads();
+        for (int t = threadIdx.x; t < T * WS_TP; t += 256) {
+            const int r = t / WS_TP, p = t % WS_TP;
+            const bool in = p0 + p < P;
+            sz[r * LD + p] = (in && r < Co) ? __ldg(dz + ((size_t)b * Co + r) * P + p0 + p) : 0.f;
+            float v = 0.f;
+            if (in && r < Ci) v = (r < C1) ? __ldg(x1 + ((size_t)b * C1 + r) * P + p0 + p) : __ldg(x2 + ((size_t)b * C2 + (r - C1)) * P + p0 + p);
+            sx[r * LD + p] = v;
+        }
+        __syncthreads();
+#pragma unroll 4
+        for (int p = 0; p < WS_TP; p += 4) {
+            float4 a[R], c[R];
+#pragma unroll
+            for (int i = 0; i < R; ++i) {
+                a[i] = *reinterpret_cast<const float4 *>(sz + (R * ty + i) * LD + p);
+                c[i] = *reinterpret_cast<const float4 *>(sx + (R * tx + i) * LD + p);
+            }
+#pragma unroll
+            for (int i = 0; i < R; ++i)
+#pragma unroll
+                for (int j = 0; j < R; ++j)
+                    acc[i][j] = fmaf(a[i].x, c[j].x, fmaf(a[i].y, c[j].y, fmaf(a[i].z, c[j].z, fmaf(a[i].w, c[j].w, acc[i][j]))));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            const int co = R * ty + i, ci = R * tx + j;
+            if (co < Co && ci < Ci && acc[i][j] != 0.f) atomicAdd(dw + (size_t)co * Ci + ci, acc[i][j]);
+        }
 }
 
 static void split_plan(int64_t C, int64_t P, int &chunk, int &nsplit)
@@ -244,6 +342,25 @@ static void split_plan(int64_t C, int64_t P, int &chunk, int &nsplit)
     if (ch < 1024) ch = 1024;
     chunk = (int)ch;
     nsplit = (int)ceil_div(P, ch);
+}
+
+// narrow layers (Co, Ci <= 64) of ffb6d_fusion_mlp_wgrad: CUDA-core streaming reduction
+int wgrad_small_launch(const float *grad_z, const float *x1, int64_t C1, const float *x2, int64_t C2, int64_t B, int64_t Co,
+                      int64_t P, float *grad_w, cudaStream_t st_in)
+{
+    cudaStream_t st = st_in;
+    const long long slabs = ceil_div(P, WS_TP) * B;
+    const int per = (int)std::max<long long>(1, ceil_div(slabs, 4ll * num_sms()));
+    const unsigned grid = (unsigned)ceil_div(slabs, per);
+    const int64_t m = std::max<int64_t>(Co, C1 + C2);
+    if (m <= 16)
+        wgrad_small_kernel<16><<<grid, 256, 0, st>>>(grad_z, x1, (int)C1, C2 ? x2 : nullptr, (int)C2, grad_w, (int)Co, (int)P, (int)B, per);
+    else if (m <= 32)
+        wgrad_small_kernel<32><<<grid, 256, 0, st>>>(grad_z, x1, (int)C1, C2 ? x2 : nullptr, (int)C2, grad_w, (int)Co, (int)P, (int)B, per);
+    else
+        wgrad_small_kernel<64><<<grid, 256, 0, st>>>(grad_z, x1, (int)C1, C2 ? x2 : nullptr, (int)C2, grad_w, (int)Co, (int)P, (int)B, per);
+    FFB6D_LAUNCH_OK("wgrad_small_kernel");
+    return FFB6D_OK;
 }
 
 }  // namespace ffb6d
@@ -332,8 +449,15 @@ int ffb6d_att_pool_bwd(const float *f1, int64_t C1, const float *f2, int64_t C2,
     if (B == 0 || N == 0) return FFB6D_OK;
     FFB6D_CHECK_ARG(f1 && att && grad_out && grad_f1 && grad_att && (C2 == 0 || (f2 && grad_f2)), "att_pool_bwd: null pointer");
     const long long total = (long long)B * (C1 + C2) * N;
-    att_pool_bwd_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
-        f1, (int)C1, f2, (int)C2, att, grad_out, (int)N, K, grad_f1, grad_f2, grad_att, total);
+    const bool v16 = K == 16 && ((reinterpret_cast<uintptr_t>(f1) | reinterpret_cast<uintptr_t>(f2) | reinterpret_cast<uintptr_t>(att) |
+                                  reinterpret_cast<uintptr_t>(grad_f1) | reinterpret_cast<uintptr_t>(grad_f2) |
+                                  reinterpret_cast<uintptr_t>(grad_att)) & 15) == 0;
+    if (v16)
+        att_pool_bwd_kernel<16><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            f1, (int)C1, f2, (int)C2, att, grad_out, (int)N, K, grad_f1, grad_f2, grad_att, total);
+    else
+        att_pool_bwd_kernel<0><<<(unsigned)ceil_div(total, 256), 256, 0, (cudaStream_t)stream>>>(
+            f1, (int)C1, f2, (int)C2, att, grad_out, (int)N, K, grad_f1, grad_f2, grad_att, total);
     FFB6D_LAUNCH_OK("att_pool_bwd_kernel");
     return FFB6D_OK;
 }

@@ -482,6 +482,48 @@ def att_pool(f1, f2, att):
     return out
 
 
+def lfa_att_pool_fused(xyz, neigh_idx, feature, mlp1, mlp2, fc_weight, mlp_out, negative_slope=0.2):
+    """One attentive pooling of RandLA's ``Building_block`` as ONE kernel (``ffb6d_lfa_att_pool_fused``): relative
+    position encoding -> ``mlp1`` [-> ``mlp2``] -> concat with the gathered neighbour features -> ``fc`` -> softmax over
+    K -> weighted sum -> output ``mlp`` (models/RandLA/RandLANet.py:196-250); inference, BatchNorm folded.
+
+    :param xyz: ``[B,N,3]``; :param neigh_idx: ``[B,N,16]``; :param feature: ``[B,d/2,N,1]`` (or ``[B,d/2,N]``)
+    :param mlp1, mlp2, mlp_out: ``(weight [Co,Ci], scale [Co], shift [Co])`` with BatchNorm folded; ``mlp2`` may be None
+    :param fc_weight: ``[d,d]``; :return: ``[B,d_out,N,1]``"""
+    _need_cuda(xyz, "xyz")
+    _need_cuda(feature, "feature")
+    xyz = xyz.contiguous().float()
+    idx_c, i64 = _idx_arg(neigh_idx, "neigh_idx")
+    B, N, K = idx_c.shape
+    f = feature.reshape(B, feature.shape[1], N).contiguous().float()
+    Dh = f.shape[1]
+
+    def prep(layer):
+        w, sc, sh = layer
+        return w.reshape(w.shape[0], -1).contiguous().float(), sc.contiguous().float(), sh.contiguous().float()
+
+    w1, s1, t1 = prep(mlp1)
+    w2, s2, t2 = prep(mlp2) if mlp2 is not None else (None, None, None)
+    wo, so, to = prep(mlp_out)
+    wfc = fc_weight.reshape(fc_weight.shape[0], -1).contiguous().float()
+    Do = wo.shape[0]
+    if w1.shape != (Dh, 10) or wfc.shape != (2 * Dh, 2 * Dh) or wo.shape[1] != 2 * Dh or (w2 is not None and w2.shape != (Dh, Dh)):
+        raise ValueError("layer shapes do not match d/2 = %d" % Dh)
+    out = torch.empty((B, Do, N, 1), dtype=torch.float32, device=f.device)
+    with torch.cuda.device(f.device):
+        check(lib.ffb6d_lfa_att_pool_fused(
+            xyz.data_ptr(), idx_c.data_ptr(), i64, f.data_ptr(), w1.data_ptr(), s1.data_ptr(), t1.data_ptr(),
+            w2.data_ptr() if w2 is not None else None, s2.data_ptr() if w2 is not None else None,
+            t2.data_ptr() if w2 is not None else None, wfc.data_ptr(), wo.data_ptr(), so.data_ptr(), to.data_ptr(),
+            B, N, K, Dh, Do, float(negative_slope), out.data_ptr(), _stream(f.device)))
+    return out
+
+
+def lfa_fusable(d_half, k):
+    """True when :func:`lfa_att_pool_fused` covers this width / neighbour count."""
+    return int(k) == 16 and int(d_half) in (16, 32, 64)
+
+
 # --------------------------------------------------------------------------- depth -> point sets
 def backproject(depth, K, choose):
     """Depth map -> the point sets of the fusion schedule, on the GPU; replaces ``dpt_2_pcld`` +

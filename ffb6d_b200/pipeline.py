@@ -38,6 +38,9 @@ class FusionPass:
         # it overlaps the searches (issue bound) that are still running
         self.gstreams = ([torch.cuda.Stream(device=self.device, priority=prio[1])
                           for _ in range(n_gather_streams or n_streams)] if n_streams > 1 else None)
+        # grid builds: latency-bound cluster kernels, spread over streams of their own (FFB6D_BUILD_STREAMS, default 0 = share the search streams)
+        nb = int(os.environ.get("FFB6D_BUILD_STREAMS", "0"))
+        self.bstreams = [torch.cuda.Stream(device=self.device) for _ in range(nb)] if (n_streams > 1 and nb > 0) else []
         self.gathers = S.gather_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.features = []
@@ -52,8 +55,10 @@ class FusionPass:
         # (measured: a K = 16 query costs about 12 K = 1 queries)
         import os
         unlocked = {}
+        derived = S.derived_searches(S.knn_schedule(n_points, h, w, k))   # row slices of another search
         for op, key, C, Sz, Q, K in self.gathers:
             src = key.replace("cld_sub_idx", "cld_nei_idx")
+            src = derived.get(src, src)
             unlocked[src] = unlocked.get(src, 0) + S.gather_alg_bytes(C, Sz, Q, K)
         self.priority = None
         if os.environ.get("FFB6D_SCHED", "unlock") == "unlock":   # "size": largest search first (3.63 vs 3.59 ms)
@@ -67,7 +72,8 @@ class FusionPass:
     # -- the two halves of a pass ------------------------------------------------------
     def build_indices(self, cld, dpt_xyz, choose, timer=None, events=None):
         inputs = S.build_ffb6d_indices(cld, dpt_xyz, k=self.k, index_dtype=self.index_dtype,
-                                       timer=timer, streams=self.streams, events=events, priority=self.priority)
+                                       timer=timer, streams=self.streams, events=events, priority=self.priority,
+                                       build_streams=self.bstreams)
         inputs["choose"] = choose
         return inputs
 
@@ -121,7 +127,7 @@ class FusionPass:
                 # tell the caching allocator (inside a capture the graph's private pool keeps them alive)
                 inputs[key].record_stream(st)
                 outs[i].record_stream(main)
-        for st in (self.streams + self.gstreams) if events is not None else gs:
+        for st in (self.streams + self.gstreams + self.bstreams) if events is not None else gs:
             main.wait_stream(st)
         if events is not None:
             events.pop("_keepalive", None)   # every search has been joined: the grids may go
@@ -178,7 +184,8 @@ class FusionPass:
         cld, pyr = ops.backproject(depth, intr, choose)
         events = {} if self.streams is not None else None
         inputs = S.build_ffb6d_indices(cld, None, k=self.k, index_dtype=self.index_dtype, streams=self.streams,
-                                       pyramid=pyr, image_hw=(self.h, self.w), events=events, priority=self.priority)
+                                       pyramid=pyr, image_hw=(self.h, self.w), events=events, priority=self.priority,
+                                       build_streams=self.bstreams)
         inputs["choose"] = choose
         return inputs, self.run_gathers(inputs, events=events)
 

@@ -47,9 +47,17 @@ def att_pooling(sd, prefix, f1, f2):
     return ops.fusion_mlp(agg, None, w, scale, shift, negative_slope=0.2)
 
 
-def building_block(sd, prefix, xyz, feature, neigh_idx):
+def building_block(sd, prefix, xyz, feature, neigh_idx, fused=True):
     """``Building_block.forward`` (RandLANet.py:196-214): xyz [B,N,3], feature [B,d/2,N,1],
-    neigh_idx [B,N,K] -> [B,d,N,1]."""
+    neigh_idx [B,N,K] -> [B,d,N,1].  With K = 16 and d/2 in {16, 32, 64} each attentive pooling is ONE fused
+    kernel (``ops.lfa_att_pool_fused``: no [B,C,N,K] tensor touches HBM); other shapes, or ``fused=False``, run
+    the per-op kernels below."""
+    if fused and ops.lfa_fusable(feature.shape[1], neigh_idx.shape[2]):
+        m1, m2 = _conv_bn(sd, prefix + ".mlp1"), _conv_bn(sd, prefix + ".mlp2")
+        f_agg = ops.lfa_att_pool_fused(xyz, neigh_idx, feature, m1, None, sd[prefix + ".att_pooling_1.fc.weight"],
+                                       _conv_bn(sd, prefix + ".att_pooling_1.mlp"))
+        return ops.lfa_att_pool_fused(xyz, neigh_idx, f_agg, m1, m2, sd[prefix + ".att_pooling_2.fc.weight"],
+                                      _conv_bn(sd, prefix + ".att_pooling_2.mlp"))
     f_xyz = ops.relative_pos_encoding(xyz, neigh_idx, channel_major=True)           # [B,10,N,K]
     w, scale, shift = _conv_bn(sd, prefix + ".mlp1")
     f_xyz = ops.fusion_mlp(f_xyz, None, w, scale, shift, negative_slope=0.2)
@@ -59,12 +67,12 @@ def building_block(sd, prefix, xyz, feature, neigh_idx):
     return att_pooling(sd, prefix + ".att_pooling_2", _gather_cm(f_agg, neigh_idx), f_xyz)
 
 
-def dilated_res_block(sd, prefix, feature, xyz, neigh_idx):
+def dilated_res_block(sd, prefix, feature, xyz, neigh_idx, fused=True):
     """``Dilated_res_block.forward`` (RandLANet.py:179-184): feature [B,d_in,N,1] -> [B,2*d_out,N,1]."""
     p = prefix + "." if prefix else ""
     w, scale, shift = _conv_bn(sd, p + "mlp1")
     f_pc = ops.fusion_mlp(feature, None, w, scale, shift, negative_slope=0.2)
-    f_pc = building_block(sd, p + "lfa", xyz, f_pc, neigh_idx)
+    f_pc = building_block(sd, p + "lfa", xyz, f_pc, neigh_idx, fused)
     # leaky_relu(mlp2(f_pc) + shortcut(feature)): one GEMM over [f_pc; feature] with BN-scaled weights
     w2, s2, b2 = _conv_bn(sd, p + "mlp2")
     ws, ss, bs = _conv_bn(sd, p + "shortcut")

@@ -15,7 +15,7 @@ from .ops import knn_search, KnnGrid, knn_uses_grid
 
 from .tables import (RGB_DS_SR, RGB_UP_SR, PCLD_SUB_S_R, N_DS_LAYERS, N_UP_LAYERS, K_NEIGH,  # noqa: F401
                      DS_RGB_OC, DS_RNDLA_OC, UP_RGB_OC, UP_RNDLA_OC, knn_schedule, set_size, gather_schedule,
-                     fusion_mlp_schedule, knn_alg_bytes, gather_alg_bytes, frame_alg_bytes)
+                     fusion_mlp_schedule, knn_alg_bytes, gather_alg_bytes, frame_alg_bytes, derived_searches)
 
 
 def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
@@ -30,7 +30,7 @@ def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
 
 
 def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None,
-                        pyramid=None, image_hw=None, events=None, priority=None):
+                        pyramid=None, image_hw=None, events=None, priority=None, build_streams=None):
     """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
 
     :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
@@ -38,6 +38,8 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
       pass ``pyramid={2: [B,HW/4,3], 4: ..., 8: ...}`` + ``image_hw=(H, W)`` (what
       :func:`ffb6d_b200.ops.backproject` returns) and leave it None
     :param streams: optional list of side ``torch.cuda.Stream`` s to overlap the 22 searches on
+    :param build_streams: optional extra side streams for the grid builds (latency-bound cluster kernels that
+      co-run well); the caller joins them together with ``streams``
     :param priority: optional ``{index key: float}``; with ``streams`` the searches (and the grid
       builds they need) are issued in descending priority instead of descending size, so that the
       searches whose consumers are expensive finish first
@@ -90,19 +92,31 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     grids = {}
     main = torch.cuda.current_stream(cld.device)
     par = streams is not None and timer is None
+    bstreams = list(build_streams) if (build_streams and par) else []
 
     def fork():
         if par:
-            for st in streams:
+            for st in streams + bstreams:
                 st.wait_stream(main)
 
     def join():
         if par:
-            for st in streams:
+            for st in streams + bstreams:
                 main.wait_stream(st)
 
-    def on(i):
-        return torch.cuda.stream(streams[i % len(streams)]) if par else contextlib.nullcontext()
+    def on(i, pool=None):
+        pool = pool or streams
+        return torch.cuda.stream(pool[i % len(pool)]) if par else contextlib.nullcontext()
+
+    # Cloud level j is the first N_j rows of the shuffled cloud (ycb_dataset.py:278), so two searches of the same
+    # support with the same K whose query sets are cloud levels answer the same questions on a prefix: the
+    # schedule's r2p_ds_nei_idx2/3 are the first 192 / 48 rows of r2p_ds_nei_idx1 (support img8), r2p_up_nei_idx0
+    # the first rows of r2p_ds_nei_idx0 (img4), r2p_up_nei_idx1 of r2p_up_nei_idx2 (img2).  Those four searches
+    # are not run; their tensors are row slices of the larger search (identical values by construction).
+    derived = derived_searches(calls)
+    children = {}
+    for child, parent in derived.items():
+        children.setdefault(parent, []).append(child)
 
     fork()
     # a search waits only for ITS grid, a consumer only for ITS index tensor (events, not joins)
@@ -117,7 +131,7 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
         order = sorted(calls, key=lambda c: -(sets[c[2]].shape[1] * c[3])) if par else calls
         build_order = sorted(gridded, key=lambda g: -sets[g[0]].shape[1])
     for i, g in enumerate(build_order):
-        with on(i):
+        with on(i, bstreams or None):
             if timer is not None:
                 timer.start("knn_build:%s%d:k%d" % (g[0][0], g[0][1], g[1]), 0)
             grids[g] = KnnGrid(sets[g[0]], g[1])
@@ -126,6 +140,8 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             if par:
                 built[g] = torch.cuda.Event()
                 built[g].record()
+    order = [c for c in order if c[0] not in derived]
+    qsize = {key: sets[q].shape[1] for key, s, q, kk in calls}
     for i, (key, s, q, kk) in enumerate(order):
         sup, qry = sets[s], sets[q]
         with on(i):
@@ -147,6 +163,9 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
                 n_sub = sets[("cld", lvl + 1)].shape[1]
                 inputs["cld_sub_idx%d" % lvl] = inputs[key][:, :n_sub, :].contiguous()
                 done.append("cld_sub_idx%d" % lvl)
+            for child in children.get(key, ()):   # prefix slices instead of separate searches (see above)
+                inputs[child] = inputs[key][:, :qsize[child], :].contiguous()
+                done.append(child)
             if par and events is not None:
                 ev = torch.cuda.Event()
                 ev.record()

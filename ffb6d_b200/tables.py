@@ -42,6 +42,24 @@ def knn_schedule(n_points=12288, h=480, w=640, k=K_NEIGH):
     return calls
 
 
+def derived_searches(calls):
+    """``{child key: parent key}``: searches of the schedule that are row slices of another search.  Cloud level j
+    is the first N_j rows of the shuffled cloud (ycb_dataset.py:278), so two searches of the same support with the
+    same K whose query sets are cloud levels i < j answer the same questions on a prefix: ``r2p_ds_nei_idx2/3`` are
+    the first 192 / 48 rows of ``r2p_ds_nei_idx1`` (support img8), ``r2p_up_nei_idx0`` of ``r2p_ds_nei_idx0`` (img4),
+    ``r2p_up_nei_idx1`` of ``r2p_up_nei_idx2`` (img2)."""
+    by_group, derived = {}, {}
+    for key, s, q, kk in calls:
+        if q[0] == "cld":
+            by_group.setdefault((s, kk), []).append((q[1], key))
+    for members in by_group.values():
+        members.sort()
+        for lvl, key in members[1:]:
+            if lvl > members[0][0]:
+                derived[key] = members[0][1]
+    return derived
+
+
 def set_size(name, n_points=12288, h=480, w=640):
     kind, a = name
     if kind == "cld":

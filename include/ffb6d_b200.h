@@ -309,6 +309,24 @@ int ffb6d_att_pool_bwd(const float *f1, int64_t C1, const float *f2, int64_t C2,
                        const float *grad_out, int64_t B, int64_t N, int K,
                        float *grad_f1, float *grad_f2, float *grad_att, ffb6d_stream_t stream);
 
+/*
+ * One fused kernel per attentive pooling of RandLA's local feature aggregation (inference, BatchNorm folded):
+ *   f_xyz = mlp1(relative_pos_encoding(xyz, idx)) [-> mlp2]          (models/RandLA/RandLANet.py:197-199, 207, 216-223)
+ *   f_cat = cat(gather_neighbour(feature, idx), f_xyz)                (:200-205, 208-212)
+ *   out   = mlp(sum_K f_cat * softmax_K(fc(f_cat)))                   (:243-250)
+ * A warp owns a point; nothing of size N*K is written to memory.
+ *   xyz [B,N,3]; idx [B,N,16]; feature [B,Dh,N] (Dh = d/2 in {16, 32, 64}); w_x1 [Dh,10], w_x2 [Dh,Dh] or NULL
+ *   (NULL: first pooling of a Building_block), w_fc [2Dh,2Dh], w_out [Do,2Dh] (Do <= 2Dh); scale_* / shift_*: the
+ *   folded BatchNorm of mlp1 / mlp2 / the output mlp; LeakyReLU(negative_slope) after each of them.
+ *   out [B,Do,N] f32.
+ */
+int ffb6d_lfa_att_pool_fused(const float *xyz, const void *idx, int idx_is_i64, const float *feature,
+                             const float *w_x1, const float *scale_x1, const float *shift_x1,
+                             const float *w_x2, const float *scale_x2, const float *shift_x2,
+                             const float *w_fc, const float *w_out, const float *scale_out, const float *shift_out,
+                             int64_t B, int64_t N, int K, int64_t Dh, int64_t Do, float negative_slope,
+                             float *out, ffb6d_stream_t stream);
+
 /* ---- depth map -> searched point sets ------------------------------------- */
 /*
  * Back-projection of the depth image and extraction of the four point sets the fusion

@@ -50,12 +50,15 @@ def test_dilated_res_block_matches_reference(cuda, name):
     f_pc = F.fusion_mlp(feature, None, w, scale, shift, negative_slope=0.2)
     close(f_pc.cpu().numpy(), c["mlp1_out"], "mlp1")
     # local feature aggregation (relative position encoding, 2 neighbour gathers, 2 attentive poolings)
-    lfa = randla.building_block(sd, "lfa", xyz, torch.from_numpy(c["mlp1_out"]).cuda(), idx)
-    close(lfa.cpu().numpy(), c["lfa_out"], "building_block")
-    # whole block
-    out = randla.dilated_res_block(sd, "", feature, xyz, idx)
-    assert out.shape == c["out"].shape
-    close(out.cpu().numpy(), c["out"], "dilated_res_block")
+    f1 = torch.from_numpy(c["mlp1_out"]).cuda()
+    for fused in (True, False):      # one fused kernel per attentive pooling / the per-op kernels
+        lfa = randla.building_block(sd, "lfa", xyz, f1, idx, fused=fused)
+        close(lfa.cpu().numpy(), c["lfa_out"], "building_block fused=%s" % fused)
+        out = randla.dilated_res_block(sd, "", feature, xyz, idx, fused=fused)
+        assert out.shape == c["out"].shape
+        close(out.cpu().numpy(), c["out"], "dilated_res_block fused=%s" % fused)
+    # int32 indices (what the index build produces) == int64
+    assert torch.equal(randla.building_block(sd, "lfa", xyz, f1, idx.int()), randla.building_block(sd, "lfa", xyz, f1, idx))
 
 
 def test_att_pool_against_torch(cuda):

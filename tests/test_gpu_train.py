@@ -122,7 +122,7 @@ def test_att_pool_backward_vs_autograd(cuda):
 
 
 @pytest.mark.parametrize("B,C1,C2,Co,P", [(2, 64, 64, 64, 3072), (1, 36, 8, 70, 50), (3, 5, 0, 3, 7), (2, 1024, 1024, 1024, 600),
-                                          (8, 64, 64, 64, 19200)])
+                                          (8, 64, 64, 64, 19200), (2, 10, 0, 16, 98304), (2, 32, 32, 64, 1001), (1, 16, 16, 32, 3072)])
 def test_wgrad_vs_float64(cuda, B, C1, C2, Co, P):
     from ffb6d_b200._lib import lib, check
     from ffb6d_b200.ops import _stream

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=0)
+    ap.add_argument("--profile", action="store_true", help="print the per-kernel GPU time of one step (CUPTI) to stderr")
     args = ap.parse_args()
     import numpy as np
     import torch
@@ -106,6 +107,25 @@ def main():
         dist.barrier()
     ms = max(e0.elapsed_time(e1), wall)
     (ms,) = max_over_ranks([ms], device=dev)
+    if args.profile and rank == 0:
+        import collections
+        import re
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize()
+        agg = collections.OrderedDict()
+        for ev in prof.events():
+            if ev.device_type is not None and "cuda" in str(ev.device_type).lower():
+                name = re.sub(r"\(.*", "", ev.name).replace("void ", "").replace("ffb6d::", "")
+                d = agg.setdefault(name, [0, 0.0])
+                d[0] += 1
+                d[1] += ev.device_time
+        tot = sum(v[1] for v in agg.values())
+        sys.stderr.write("one step: %.2f ms of kernel time, %d launches (wall %.2f ms/step)\n"
+                         % (tot / 1e3, sum(v[0] for v in agg.values()), ms / args.steps))
+        for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1])[:25]:
+            sys.stderr.write("%-70s n=%4d %9.1f us %5.1f%%\n" % (k[:70], v[0], v[1], 100 * v[1] / tot))
     finite = bool(torch.isfinite(loss).item()) and all(torch.isfinite(p.grad).all().item() for p in model.parameters()
                                                        if p.grad is not None)
     if rank == 0:
@@ -114,7 +134,7 @@ def main():
                 + ", DDP gradient all-reduce over NCCL" * (world > 1),
                 "value": world * B * N0 * args.steps / (ms / 1e3), "unit": "points/s", "n_gpus": world,
                 "batch_per_gpu": B, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-                "params": n_params, "grad_allreduce_bytes": 4 * n_params if world > 1 else 0, "loss": float(loss),
+                "params": n_params, "grad_allreduce_bytes": 4 * n_params if world > 1 else 0, "loss": float(loss.detach()),
                 "finite": finite, "dtype": "f32", "data": "synthetic", "scaling": "weak"}
         print(json.dumps(line))
     if world > 1:
