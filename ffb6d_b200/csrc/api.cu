@@ -60,6 +60,7 @@ const Env &env()
         auto on = [](const char *n) { const char *x = getenv(n); return x && *x && strcmp(x, "0") != 0; };
         v.gather_direct = on("FFB6D_GATHER_DIRECT");
         v.mlp_no_direct = on("FFB6D_MLP_NO_DIRECT");
+        v.mlp_no_pair_tiles = on("FFB6D_MLP_NO_MT2");
         v.check_indices = on("FFB6D_CHECK_INDICES");
         v.grid_thread_search = on("FFB6D_GRID_THREAD_SEARCH");
         v.knn_max_ctas = getenv("FFB6D_KNN_MAX_CTAS") ? atoi(getenv("FFB6D_KNN_MAX_CTAS")) : 0;

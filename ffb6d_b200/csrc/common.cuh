@@ -79,6 +79,7 @@ int wgrad_small_launch(const float *grad_z, const float *x1, int64_t C1, const f
 struct Env {
     bool gather_direct;     // FFB6D_GATHER_DIRECT=1: K-lane gathers through the older direct kernel
     bool mlp_no_direct;     // FFB6D_MLP_NO_DIRECT=1
+    bool mlp_no_pair_tiles; // FFB6D_MLP_NO_MT2=1: one 128-row weight tile per CTA for every layer (A/B timing)
     bool check_indices;     // FFB6D_CHECK_INDICES=1: validate gather indices (synchronises; debugging aid)
     bool grid_thread_search;
     int knn_max_ctas;       // FFB6D_KNN_MAX_CTAS=n: cap the search kernels at n CTAs per SM (leaves registers and warp

@@ -127,7 +127,8 @@ struct MlpEpilogue {
     int out_nsc;
 };
 constexpr int mlp2_threads(int nsw) { return (nsw + 2) * 32; }   // staging warps + producer + issuer
-constexpr int mlp2_smem(int nst) { return nst * STAGE_BYTES + 128; }
+constexpr int mlp2_stage(int mt) { return (2 * mt + 2) * TILE_BYTES; }           // MT x [A_hi | A_lo], B_hi, B_lo
+constexpr int mlp2_smem(int nst, int mt = 1) { return nst * mlp2_stage(mt) + 128; }
 
 __global__ void __launch_bounds__(256)
 fusion_mlp_pack_kernel(const float *__restrict__ w, int Co, int Ci, int nk, int nblocks, float4 *__restrict__ packed)
@@ -156,24 +157,31 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(bar) : "memory");
 }
 
-template <int NST, bool DIRECT, int NSW, int PD>
+// MT = 128-row tiles of W per CTA (1 or 2).  With MT = 2 a CTA multiplies ONE staged activation tile with two weight
+// tiles (256 output channels): the activation split + staging -- the instruction-bound part of this kernel, repeated
+// by every row tile of a layer -- halves per FLOP; all 512 TMEM columns are in use (2 row tiles x 2 chunk buffers).
+template <int NST, bool DIRECT, int NSW, int PD, int MT = 1>
 __global__ void __launch_bounds__(mlp2_threads(NSW), DIRECT ? 3 : 1)
 fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__restrict__ x2, int C2,
                          const unsigned char *__restrict__ wpack, const float *__restrict__ scale,
                          const float *__restrict__ shift, float *__restrict__ out, int Co, int P, int act,
                          float slope, MlpEpilogue ep)
 {
+    static_assert(MT == 1 || !DIRECT, "the single-chunk variant keeps one row tile");
+    constexpr int STAGE = mlp2_stage(MT);
+    constexpr int TMEM_COLS = DIRECT ? TN : 2 * TN * MT;
     extern __shared__ __align__(1024) unsigned char smem[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * STAGE_BYTES);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + NST * STAGE);
     uint64_t *full_a = bars, *full_b = bars + NST, *empty = bars + 2 * NST, *chunk = bars + 3 * NST;   // 11 barriers
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NST * STAGE_BYTES + 96);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(smem + NST * STAGE + 96);
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int b = blockIdx.z, m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+    const int b = blockIdx.z, m0 = blockIdx.y * TM * MT, n0 = blockIdx.x * TN;
+    const int mt_valid = min(MT, (Co - m0 + TM - 1) / TM);   // row tiles of this CTA that exist
     const int Ci = C1 + C2;
     const int nk = (Ci + TK - 1) / TK;
 
     if (wid == 0) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(DIRECT ? TN : 2 * TN));
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(tmem_slot)), "r"(TMEM_COLS));
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
     }
     if (tid == 32) {
@@ -194,15 +202,16 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
     if (wid == NSW) {
         // ---------------- A producer
         if (lane == 0) {
-            const unsigned char *src = wpack + (size_t)blockIdx.y * nk * PACK_BLOCK_BYTES;
+            const unsigned char *src = wpack + (size_t)blockIdx.y * MT * nk * PACK_BLOCK_BYTES;
             for (int kt = 0; kt < nk; ++kt) {
                 const int st = kt % NST, n = kt / NST;
                 if (n >= 1) mbar_wait(smem_u32(empty + st), (uint32_t)((n - 1) & 1));
                 const uint32_t bar = smem_u32(full_a + st);
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(PACK_BLOCK_BYTES) : "memory");
-                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                             :: "r"(smem_u32(smem + st * STAGE_BYTES)), "l"(src + (size_t)kt * PACK_BLOCK_BYTES),
-                                "r"(PACK_BLOCK_BYTES), "r"(bar) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(mt_valid * PACK_BLOCK_BYTES) : "memory");
+                for (int mt = 0; mt < mt_valid; ++mt)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 :: "r"(smem_u32(smem + st * STAGE + mt * PACK_BLOCK_BYTES)),
+                                    "l"(src + ((size_t)mt * nk + kt) * PACK_BLOCK_BYTES), "r"(PACK_BLOCK_BYTES), "r"(bar) : "memory");
             }
         }
         __syncwarp();
@@ -216,16 +225,21 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 // this lane shares its scheduler with four staging warps: keep its per-tile instruction
                 // count small (one descriptor per operand tile, the k-steps are +256 in the address field)
-                const uint32_t a_hi = smem_u32(smem + st * STAGE_BYTES);
-                const uint64_t da_hi = umma_desc(a_hi), da_lo = umma_desc(a_hi + TILE_BYTES);
-                const uint64_t db_hi = umma_desc(a_hi + 2 * TILE_BYTES), db_lo = umma_desc(a_hi + 3 * TILE_BYTES);
-                const uint32_t d_buf = tmem_d + (uint32_t)(((kt / CH) & 1) * TN);
+                const uint32_t s0 = smem_u32(smem + st * STAGE);
+                const uint64_t db_hi = umma_desc(s0 + 2 * MT * TILE_BYTES), db_lo = umma_desc(s0 + (2 * MT + 1) * TILE_BYTES);
 #pragma unroll
-                for (int j = 0; j < TK / 8; ++j) {
-                    const uint64_t off = (uint64_t)(j * ((2 * CHUNK_BYTES) >> 4));
-                    umma_tf32(d_buf, da_hi + off, db_hi + off, (kt % CH != 0 || j > 0) ? 1u : 0u);
-                    umma_tf32(d_buf, da_lo + off, db_hi + off, 1u);
-                    umma_tf32(d_buf, da_hi + off, db_lo + off, 1u);
+                for (int mt = 0; mt < MT; ++mt) {
+                    if (mt < mt_valid) {
+                        const uint64_t da_hi = umma_desc(s0 + mt * PACK_BLOCK_BYTES), da_lo = umma_desc(s0 + mt * PACK_BLOCK_BYTES + TILE_BYTES);
+                        const uint32_t d_buf = tmem_d + (uint32_t)((mt * 2 + ((kt / CH) & 1)) * TN);
+#pragma unroll
+                        for (int j = 0; j < TK / 8; ++j) {
+                            const uint64_t off = (uint64_t)(j * ((2 * CHUNK_BYTES) >> 4));
+                            umma_tf32(d_buf, da_hi + off, db_hi + off, (kt % CH != 0 || j > 0) ? 1u : 0u);
+                            umma_tf32(d_buf, da_lo + off, db_hi + off, 1u);
+                            umma_tf32(d_buf, da_hi + off, db_lo + off, 1u);
+                        }
+                    }
                 }
                 asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                              :: "r"(smem_u32(empty + st)) : "memory");
@@ -244,9 +258,11 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                          ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
         constexpr int COLS = 4 * TN / NSW, NI = COLS / 32;   // accumulator columns per thread: 64 or 32
         const int q = wid & 3, cs = wid >> 2;                 // TMEM lane quarter (fixed by the warp id), column slice
-        float acc[DIRECT ? 1 : COLS];
+        float acc[MT][DIRECT ? 1 : COLS];
 #pragma unroll
-        for (int i = 0; i < (DIRECT ? 1 : COLS); ++i) acc[i] = 0.f;
+        for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+            for (int i = 0; i < (DIRECT ? 1 : COLS); ++i) acc[mt][i] = 0.f;
         // columns COLS*cs + 32*i .. +31 of accumulator `buf`, this thread's row
         auto tmem_load32 = [&](int buf, int i, uint32_t (&v)[32]) {
             const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + COLS * cs + 32 * i);
@@ -267,9 +283,11 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 mbar_wait(smem_u32(chunk + buf), (uint32_t)((c >> 1) & 1));
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
+                for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
                 for (int i = 0; i < COLS / 16; ++i) {   // 16 columns at a time keeps the temporaries small
                     uint32_t v[16];
-                    const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)(buf * TN + COLS * cs + 16 * i);
+                    const uint32_t taddr = tmem_d + ((uint32_t)(32 * q) << 16) + (uint32_t)((mt * 2 + buf) * TN + COLS * cs + 16 * i);
                     asm volatile(
                         "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
                         "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
@@ -278,7 +296,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                         : "r"(taddr));
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) acc[16 * i + j] = __fadd_rn(acc[16 * i + j], __uint_as_float(v[j]));
+                    for (int j = 0; j < 16; ++j) acc[mt][16 * i + j] = __fadd_rn(acc[mt][16 * i + j], __uint_as_float(v[j]));
                 }
                 asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             }
@@ -325,7 +343,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
             }
         };
         auto store_b = [&](int st, const ldt (&rb)[4]) {
-            unsigned char *sB_hi = smem + st * STAGE_BYTES + 2 * TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
+            unsigned char *sB_hi = smem + st * STAGE + 2 * MT * TILE_BYTES, *sB_lo = sB_hi + TILE_BYTES;
             unsigned char *bh = sB_hi + kg * CHUNK_BYTES + nl * 16, *bl = sB_lo + kg * CHUNK_BYTES + nl * 16;
             float4 hi, lo;
             if constexpr (NSW == 8) {
@@ -384,7 +402,9 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
         } else {
             drain((nk - 1) / CH);
         }
-        const int gm = m0 + 32 * q + lane;
+#pragma unroll
+        for (int mt = 0; mt < MT; ++mt) {
+        const int gm = m0 + mt * TM + 32 * q + lane;
         const bool row_ok = gm < Co;
         const float sc = row_ok ? __ldg(scale + gm) : 0.f, sh = row_ok ? __ldg(shift + gm) : 0.f;
         float *orow = out + ((size_t)b * Co + (row_ok ? gm : 0)) * P;
@@ -401,7 +421,7 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 tmem_load32(0, i, v);   // warp-collective: rows beyond Co take part, they just do not store
             } else {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[32 * i + j]);
+                for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(acc[mt][32 * i + j]);
             }
             if (row_ok) {
 #pragma unroll
@@ -439,10 +459,11 @@ fusion_mlp_packed_kernel(const float *__restrict__ x1, int C1, const float *__re
                 }
             }
         }
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(DIRECT ? TN : 2 * TN));
+    if (wid == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "r"(DIRECT ? TN : 2 * TN * MT));
 }
 
 
@@ -677,8 +698,10 @@ extern "C" int ffb6d_fusion_mlp_fwd_ex(const float *x1, int64_t C1, const float 
     FFB6D_CHECK_ARG(!addend || (NA >= 1 && NA < (1ll << 31)), "fusion_mlp_fwd: bad addend length");
     {
         auto k_big = fusion_mlp_packed_kernel<3, false, 16, 3>;
+        auto k_big2 = fusion_mlp_packed_kernel<2, false, 16, 2, 2>;
         auto k_direct = fusion_mlp_packed_kernel<1, true, 8, 2>;
         FFB6D_OPTIN_SMEM(k_big, mlp2_smem(3));
+        FFB6D_OPTIN_SMEM(k_big2, mlp2_smem(2, 2));
         FFB6D_OPTIN_SMEM(k_direct, mlp2_smem(1));
     }
     MlpEpilogue ep;
@@ -692,7 +715,12 @@ extern "C" int ffb6d_fusion_mlp_fwd_ex(const float *x1, int64_t C1, const float 
         fusion_mlp_packed_kernel<1, true, 8, 2><<<grid, mlp2_threads(8), mlp2_smem(1), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
             act, negative_slope, ep);
-    else
+    else if (Co > TM && !env().mlp_no_pair_tiles) {   // two row tiles per CTA: one staged activation tile feeds 256 output channels
+        dim3 grid2(grid.x, (unsigned)ceil_div(ceil_div(Co, TM), 2), grid.z);
+        fusion_mlp_packed_kernel<2, false, 16, 2, 2><<<grid2, mlp2_threads(16), mlp2_smem(2, 2), (cudaStream_t)stream>>>(
+            x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
+            act, negative_slope, ep);
+    } else
         fusion_mlp_packed_kernel<3, false, 16, 3><<<grid, mlp2_threads(16), mlp2_smem(3), (cudaStream_t)stream>>>(
             x1, (int)C1, C2 ? x2 : nullptr, (int)C2, (const unsigned char *)packed, scale, shift, out, (int)Co, (int)P,
             act, negative_slope, ep);

@@ -29,51 +29,71 @@ constexpr int LK = 16;   // neighbours per point (the only K FFB6D uses, dataset
 
 __device__ __forceinline__ float leaky(float v, float slope) { return v > 0.f ? v : v * slope; }
 
-// out[c][k] = act(scale[c] * sum_j Wt[j][c] * in[j][k] + shift[c]) for c < COUT, k < 16, by one warp.
-// in / out: shared memory [*][16]; Wt: shared memory, transposed [CIN][COUT]; act < 0: no affine, no activation.
-// COUT >= 32: lane owns channels lane + 32m and all 16 positions; COUT == 16: lane owns channel lane % 16 and
-// 8 positions (half = lane / 16).
+constexpr int LD = 20;   // shared-memory row stride of a [channels][16 positions] tile: 80 bytes, so that the 128-bit
+                         // row accesses of lanes one row apart fall into distinct banks (a 64-byte stride is 4-way conflicted)
+
+template <int N>
+__device__ __forceinline__ void lds_vec(const float *p, float (&w)[N])   // N consecutive floats, N-float aligned
+{
+    if constexpr (N == 1) {
+        w[0] = p[0];
+    } else if constexpr (N == 2) {
+        const float2 v = *reinterpret_cast<const float2 *>(p);
+        w[0] = v.x; w[1] = v.y;
+    } else {
+#pragma unroll
+        for (int q = 0; q < N / 4; ++q) {
+            const float4 v = *reinterpret_cast<const float4 *>(p + 4 * q);
+            w[4 * q] = v.x; w[4 * q + 1] = v.y; w[4 * q + 2] = v.z; w[4 * q + 3] = v.w;
+        }
+    }
+}
+
+// acc[i][k] = sum_j Wt[j][CPL*l + i] * in[j][8*half + k]: the warp's 16 x COUT product, lane (l = lane % 16, half =
+// lane / 16) owning CPL = COUT / 16 consecutive output channels and 8 of the 16 positions.  Per j: two broadcast
+// 128-bit activation loads and ONE weight load of CPL floats feed 8 * CPL FMAs.
+template <int COUT>
+__device__ __forceinline__ void warp_mac16(const float *__restrict__ Wt, int cin, const float *__restrict__ in, int lane,
+                                           float (&acc)[COUT / 16][8])
+{
+    constexpr int CPL = COUT / 16;
+    const int l = lane & 15, k0 = (lane >> 4) * 8;
+#pragma unroll
+    for (int i = 0; i < CPL; ++i)
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+#pragma unroll 2
+    for (int j = 0; j < cin; ++j) {
+        float f[8], w[CPL];
+        lds_vec<8>(in + j * LD + k0, f);
+        lds_vec<CPL>(Wt + j * COUT + CPL * l, w);
+#pragma unroll
+        for (int i = 0; i < CPL; ++i)
+#pragma unroll
+            for (int k = 0; k < 8; ++k) acc[i][k] = fmaf(w[i], f[k], acc[i][k]);
+    }
+}
+
+// out[c][k] = leaky(scale[c] * (Wt^T in)[c][k] + shift[c]) for c < COUT, k < 16 (shared memory, row stride LD)
 template <int COUT>
 __device__ __forceinline__ void warp_dense16(const float *__restrict__ Wt, int cin, const float *__restrict__ in,
                                              float *__restrict__ out, const float *__restrict__ scale,
-                                             const float *__restrict__ shift, float slope, bool affine, int lane)
+                                             const float *__restrict__ shift, float slope, int lane)
 {
-    constexpr int M = COUT >= 32 ? COUT / 32 : 1;        // channels per lane
-    constexpr int KB = COUT >= 32 ? LK : LK / 2;         // positions per lane
-    const int c0 = COUT >= 32 ? lane : (lane & 15);
-    const int k0 = COUT >= 32 ? 0 : (lane >> 4) * KB;
-    float acc[M][KB];
+    constexpr int CPL = COUT / 16;
+    float acc[CPL][8];
+    warp_mac16<COUT>(Wt, cin, in, lane, acc);
+    const int l = lane & 15, k0 = (lane >> 4) * 8;
 #pragma unroll
-    for (int m = 0; m < M; ++m)
+    for (int i = 0; i < CPL; ++i) {
+        const int c = CPL * l + i;
+        const float sc = scale[c], sh = shift[c];
 #pragma unroll
-        for (int k = 0; k < KB; ++k) acc[m][k] = 0.f;
-    for (int j = 0; j < cin; ++j) {
-        float f[KB];
-#pragma unroll
-        for (int q = 0; q < KB / 4; ++q) {
-            const float4 v = *reinterpret_cast<const float4 *>(in + j * LK + k0 + 4 * q);
-            f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
-        }
-#pragma unroll
-        for (int m = 0; m < M; ++m) {
-            const float w = Wt[j * COUT + c0 + 32 * m];
-#pragma unroll
-            for (int k = 0; k < KB; ++k) acc[m][k] = fmaf(w, f[k], acc[m][k]);
-        }
-    }
-#pragma unroll
-    for (int m = 0; m < M; ++m) {
-        const int c = c0 + 32 * m;
-        const float sc = affine ? scale[c] : 1.f, sh = affine ? shift[c] : 0.f;
-#pragma unroll
-        for (int q = 0; q < KB / 4; ++q) {
+        for (int q = 0; q < 2; ++q) {
             float4 v;
-            v.x = acc[m][4 * q]; v.y = acc[m][4 * q + 1]; v.z = acc[m][4 * q + 2]; v.w = acc[m][4 * q + 3];
-            if (affine) {
-                v.x = leaky(fmaf(v.x, sc, sh), slope); v.y = leaky(fmaf(v.y, sc, sh), slope);
-                v.z = leaky(fmaf(v.z, sc, sh), slope); v.w = leaky(fmaf(v.w, sc, sh), slope);
-            }
-            *reinterpret_cast<float4 *>(out + c * LK + k0 + 4 * q) = v;
+            v.x = leaky(fmaf(acc[i][4 * q], sc, sh), slope); v.y = leaky(fmaf(acc[i][4 * q + 1], sc, sh), slope);
+            v.z = leaky(fmaf(acc[i][4 * q + 2], sc, sh), slope); v.w = leaky(fmaf(acc[i][4 * q + 3], sc, sh), slope);
+            *reinterpret_cast<float4 *>(out + c * LD + k0 + 4 * q) = v;
         }
     }
 }
@@ -125,11 +145,11 @@ lfa_att_pool_fused_kernel(const LfaParams P)
     __syncthreads();
     // ---- per-warp scratch: R [10][16] (padded to 12 rows), X [DH][16], FC [D][16] (gathered | encoded), A [D]
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    constexpr int WARP_FLOATS = 12 * LK + DH * LK + D * LK + D;
+    constexpr int WARP_FLOATS = 12 * LD + DH * LD + D * LD + D;
     float *R = warp_mem + (size_t)wid * WARP_FLOATS;
-    float *X = R + 12 * LK;
-    float *FC = X + DH * LK;
-    float *A = FC + D * LK;
+    float *X = R + 12 * LD;
+    float *FC = X + DH * LD;
+    float *A = FC + D * LD;
     const float slope = P.slope;
     for (long long p = (long long)blockIdx.x * WARPS + wid; p < P.total; p += (long long)gridDim.x * WARPS) {
         const int b = (int)(p / P.N), n = (int)(p % P.N);
@@ -143,10 +163,10 @@ lfa_att_pool_fused_kernel(const LfaParams P)
             const float nx = __ldg(pn), ny = __ldg(pn + 1), nz = __ldg(pn + 2);
             const float dx = __fsub_rn(cx, nx), dy = __fsub_rn(cy, ny), dz = __fsub_rn(cz, nz);
             const float ss = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-            R[0 * LK + lane] = __fsqrt_rn(ss);
-            R[1 * LK + lane] = dx; R[2 * LK + lane] = dy; R[3 * LK + lane] = dz;
-            R[4 * LK + lane] = cx; R[5 * LK + lane] = cy; R[6 * LK + lane] = cz;
-            R[7 * LK + lane] = nx; R[8 * LK + lane] = ny; R[9 * LK + lane] = nz;
+            R[0 * LD + lane] = __fsqrt_rn(ss);
+            R[1 * LD + lane] = dx; R[2 * LD + lane] = dy; R[3 * LD + lane] = dz;
+            R[4 * LD + lane] = cx; R[5 * LD + lane] = cy; R[6 * LD + lane] = cz;
+            R[7 * LD + lane] = nx; R[8 * LD + lane] = ny; R[9 * LD + lane] = nz;
         }
         // ---- neighbours' features: FC[c][k] = feature[b, c, idx[k]]  (lane = (k, half), channels c = half + 2i)
         {
@@ -154,60 +174,46 @@ lfa_att_pool_fused_kernel(const LfaParams P)
             const int col = __shfl_sync(0xffffffffu, nb, k);
             const float *fb = P.feature + (size_t)b * DH * P.N + col;
 #pragma unroll 4
-            for (int c = h; c < DH; c += 2) FC[c * LK + k] = __ldg(fb + (size_t)c * P.N);
+            for (int c = h; c < DH; c += 2) FC[c * LD + k] = __ldg(fb + (size_t)c * P.N);
         }
         __syncwarp();
         // ---- encoding MLP(s): f_xyz = mlp1(R) [-> mlp2], written as the second half of FC
         if (P.w_x2) {
-            warp_dense16<DH>(Wx1, 10, R, X, aff, aff + DH, slope, true, lane);
+            warp_dense16<DH>(Wx1, 10, R, X, aff, aff + DH, slope, lane);
             __syncwarp();
-            warp_dense16<DH>(Wx2, DH, X, FC + DH * LK, aff + 2 * DH, aff + 3 * DH, slope, true, lane);
+            warp_dense16<DH>(Wx2, DH, X, FC + DH * LD, aff + 2 * DH, aff + 3 * DH, slope, lane);
         } else {
-            warp_dense16<DH>(Wx1, 10, R, FC + DH * LK, aff, aff + DH, slope, true, lane);
+            warp_dense16<DH>(Wx1, 10, R, FC + DH * LD, aff, aff + DH, slope, lane);
         }
         __syncwarp();
-        // ---- attention scores fc(f_cat) [D][16], softmax over the neighbours, weighted sum (in registers)
+        // ---- attention scores fc(f_cat) [D][16], softmax over the neighbours, weighted sum: a lane holds CPL channels x 8
+        // positions in registers; the other 8 positions of a channel sit in the partner lane (lane ^ 16)
         {
-            constexpr int M = D / 32;
-            float acc[M][LK];
+            constexpr int CPL = D / 16;
+            float acc[CPL][8];
+            warp_mac16<D>(Wfc, D, FC, lane, acc);
+            const int l = lane & 15, k0 = (lane >> 4) * 8;
 #pragma unroll
-            for (int m = 0; m < M; ++m)
+            for (int i = 0; i < CPL; ++i) {
+                const int c = CPL * l + i;
+                float mx = acc[i][0];
 #pragma unroll
-                for (int k = 0; k < LK; ++k) acc[m][k] = 0.f;
-            for (int j = 0; j < D; ++j) {
-                float f[LK];
-#pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = *reinterpret_cast<const float4 *>(FC + j * LK + 4 * q);
-                    f[4 * q] = v.x; f[4 * q + 1] = v.y; f[4 * q + 2] = v.z; f[4 * q + 3] = v.w;
-                }
-#pragma unroll
-                for (int m = 0; m < M; ++m) {
-                    const float w = Wfc[j * D + lane + 32 * m];
-#pragma unroll
-                    for (int k = 0; k < LK; ++k) acc[m][k] = fmaf(w, f[k], acc[m][k]);
-                }
-            }
-#pragma unroll
-            for (int m = 0; m < M; ++m) {
-                const int c = lane + 32 * m;
-                float mx = acc[m][0];
-#pragma unroll
-                for (int k = 1; k < LK; ++k) mx = fmaxf(mx, acc[m][k]);
+                for (int k = 1; k < 8; ++k) mx = fmaxf(mx, acc[i][k]);
+                mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 16));
                 float den = 0.f;
 #pragma unroll
-                for (int k = 0; k < LK; ++k) {
-                    acc[m][k] = expf(acc[m][k] - mx);
-                    den += acc[m][k];
+                for (int k = 0; k < 8; ++k) {
+                    acc[i][k] = expf(acc[i][k] - mx);
+                    den += acc[i][k];
                 }
+                den += __shfl_xor_sync(0xffffffffu, den, 16);
+                float f[8];
+                lds_vec<8>(FC + c * LD + k0, f);
                 float num = 0.f;
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                    const float4 v = *reinterpret_cast<const float4 *>(FC + c * LK + 4 * q);
-                    num += v.x * (acc[m][4 * q] / den) + v.y * (acc[m][4 * q + 1] / den) + v.z * (acc[m][4 * q + 2] / den) +
-                           v.w * (acc[m][4 * q + 3] / den);
-                }
-                A[c] = num;
+                for (int k = 0; k < 8; ++k) num += f[k] * (acc[i][k] / den);
+                num += __shfl_xor_sync(0xffffffffu, num, 16);
+                if (lane < 16) A[c] = num;
             }
         }
         __syncwarp();
@@ -226,7 +232,7 @@ template <int D, int WARPS>
 static size_t lfa_smem_bytes()
 {
     constexpr int DH = D / 2;
-    return sizeof(float) * ((size_t)2 * D * D + 10 * DH + DH * DH + 4 * DH + 2 * D + (size_t)WARPS * (12 * LK + DH * LK + D * LK + D));
+    return sizeof(float) * ((size_t)2 * D * D + 10 * DH + DH * DH + 4 * DH + 2 * D + (size_t)WARPS * (12 * LD + DH * LD + D * LD + D));
 }
 
 template <int D, int WARPS>
