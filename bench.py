@@ -692,12 +692,73 @@ def main():
                                 "poolings, 6 conv+BN layers each) on this package's kernels, inference, eager launches",
                         "ms_per_step": lfa_ms, "gather_alg_bytes_per_frame": lfa_bytes,
                         "gather_model_GBps": lfa_bytes * B / (lfa_ms / 1e3) / 1e9,
-                        "note": "per-op kernels: the [B,C,N,K] neighbour / attention tensors still pass through HBM "
-                                "(a fused gather -> fc -> softmax-pool -> mlp kernel is the open row f-2)"}
+                        "note": "each attentive pooling is ONE kernel (ffb6d_lfa_att_pool_fused: neighbour gather, position "
+                                "MLP, concat, fc, softmax over K, weighted sum, output conv+BN+LeakyReLU in shared memory); "
+                                "the [B,C,N,K] neighbour / attention tensors never reach HBM (SURVEY.md §8 f-2)"}
             del blocks, feats_
             torch.cuda.empty_cache()
         except Exception as e:                      # noqa: BLE001
             lfa_line = {"error": str(e)[:300]}
+
+    # ---- the step after the network: keypoint voting of one object, 8 keypoints + centre,
+    # every one of the object's points voting; timed beside the reference's algorithm in stock torch ops
+    # (utils/meanshift_pytorch.py:33-57: N x N matrices, a host sync per iteration, one call per vote set)
+    pose_line = None
+    if world == 1 and not args.no_mlp:
+        try:
+            import math as _m
+            from ffb6d_b200 import ops as F
+            n_obj, n_sets, bw_ = 4096, 9, 0.04
+            gp = torch.Generator().manual_seed(0)
+            truth = torch.rand(n_sets, 1, 3, generator=gp) * 0.3 + torch.tensor([0.0, 0.0, 0.8])
+            votes = truth + torch.randn(n_sets, n_obj, 3, generator=gp) * 0.01
+            votes[:, ::7] += torch.rand(n_sets, (n_obj + 6) // 7, 3, generator=gp) * 0.4 - 0.2
+            votes = votes.to(dev)
+
+            def torch_fit(A):
+                n = A.shape[0]
+                C, it = A.clone(), 0
+                while True:
+                    it += 1
+                    dis = torch.norm(C.reshape(1, n, 3) - C.reshape(n, 1, 3), dim=2)
+                    w = (torch.exp(-0.5 * (dis / bw_) ** 2) / (bw_ * _m.sqrt(2 * _m.pi))).reshape(n, n, 1)
+                    new_C = torch.sum(w * C, dim=1) / torch.sum(w, dim=1)
+                    done = torch.max(torch.norm(new_C - C, dim=1)) < bw_ * 1e-3 or it > 300
+                    C = new_C
+                    if done:
+                        break
+                dis = torch.norm(C.view(n, 1, 3) - C.view(1, n, 3), dim=2)
+                mi = torch.max(torch.sum(dis < bw_, dim=1), 0)[1]
+                return C[mi]
+
+            def timed(fn, reps):
+                fn()
+                torch.cuda.synchronize()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record()
+                for _ in range(reps):
+                    fn()
+                b_.record()
+                torch.cuda.synchronize()
+                return a_.elapsed_time(b_) / reps
+
+            ours_ms = timed(lambda: F.mean_shift_fit(votes, None, bw_, 300), 3)
+            c_ours, _, it_ours = F.mean_shift_fit(votes, None, bw_, 300)
+            torch_ms = timed(lambda: [torch_fit(votes[g_]) for g_ in range(n_sets)], 1)
+            c_torch = torch.stack([torch_fit(votes[g_]) for g_ in range(n_sets)])
+            rounds = int(it_ours.max().item())
+            pose_line = {"what": "keypoint voting of one object: %d vote sets x %d points, Gaussian mean shift (bandwidth 0.04) "
+                                 "to the reference's stop rule, one persistent kernel" % (n_sets, n_obj),
+                         "ms_per_object": ours_ms, "rounds": rounds,
+                         "pair_updates_per_s": float(it_ours.sum().item()) * n_obj * n_obj / (ours_ms / 1e3),
+                         "torch_ops_ms_per_object": torch_ms, "speedup_vs_torch_ops": torch_ms / ours_ms,
+                         "max_centre_diff_m": float((c_ours - c_torch).abs().max().item()),
+                         "note": "exp-bound (one MUFU.EX2 + ~11 FP32 per pair), not HBM-bound: the modes stay in L2; the "
+                                 "comparator is the reference's algorithm in stock torch ops on this GPU"}
+            del votes
+            torch.cuda.empty_cache()
+        except Exception as e:                      # noqa: BLE001
+            pose_line = {"error": str(e)[:300]}
 
     # ---- comparators on the same box.  C5: the reference's own torch expressions
     # (models/ffb6d.py:159-194, restated in _torch_cpu_random_sample) on THIS GPU with the same features and
@@ -798,7 +859,7 @@ def main():
                              "enqueue a step" % (spin_ms / steps, enqueue_ms / steps),
         "digest_ok": digest_ok, "reference_digest_ok": reference_digest_ok,
         "roofline": roofline, "compute": compute, "pass_roofline": pass_roofline,
-        "fusion_mlps": mlp_line, "fusion_stack": stack_line, "lfa_blocks": lfa_line, "cpu_baseline": cpu_baseline, "gpu_torch_reference": gpu_torch,
+        "fusion_mlps": mlp_line, "fusion_stack": stack_line, "lfa_blocks": lfa_line, "pose_voting": pose_line, "cpu_baseline": cpu_baseline, "gpu_torch_reference": gpu_torch,
         "host_api": host_api, "clocks": clocks,
     }
     emit(line)

@@ -11,6 +11,8 @@ Public surface (same names and argument meaning as the reference, ethnhe/FFB6D):
 * :func:`grid_sub_sampling` -- ``DataProcessing.grid_sub_sampling`` (helper_tool.py:199-219)
 * :func:`build_ffb6d_indices` -- the 22-call KNN schedule of the datasets
   (datasets/ycb/ycb_dataset.py:269-309) run on the GPU in one go.
+* :mod:`ffb6d_b200.pose` -- ``MeanShiftTorch``, ``best_fit_transform``, ``cal_frame_poses(_lm)``
+  (utils/meanshift_pytorch.py:27-57, utils/pvn3d_eval_utils_kpls.py:28-160, 220-284): keypoint voting on the GPU.
 * :mod:`ffb6d_b200.modules` -- ``nn.Module`` twins of the fusion ``Conv2d`` and of RandLA's
   ``Att_pooling`` / ``Building_block`` / ``Dilated_res_block`` (reference parameter names).
 
@@ -24,13 +26,13 @@ import importlib
 
 _OPS = ("knn_search", "random_sample", "nearest_interpolation", "gather_neighbour", "relative_pos_encoding",
         "choose_gather", "grid_sub_sampling", "KnnGrid", "backproject", "fusion_mlp", "fusion_mlp_pack",
-        "PackedWeight", "fold_batchnorm", "att_pool", "sample_valid_pixels", "check_indices")
+        "PackedWeight", "fold_batchnorm", "att_pool", "sample_valid_pixels", "check_indices", "mean_shift_fit", "best_fit_transform")
 _SCHEDULE = ("build_ffb6d_indices", "build_ffb6d_indices_from_depth", "build_ffb6d_indices_native")
 _TABLES = ("knn_schedule", "gather_schedule", "fusion_mlp_schedule")
 _SUBMODULES = ("ops", "schedule", "tables", "synthetic", "pipeline", "randla", "modules", "fusion", "dist",
-               "helper_tool", "model", "_lib")
+               "helper_tool", "model", "pose", "_lib")
 
-__all__ = list(_OPS + _SCHEDULE + _TABLES) + ["randla", "modules", "fusion", "DataProcessing"]
+__all__ = list(_OPS + _SCHEDULE + _TABLES) + ["randla", "modules", "fusion", "pose", "DataProcessing"]
 
 
 def __getattr__(name):   # PEP 562: the CUDA library is loaded by the first op that is touched

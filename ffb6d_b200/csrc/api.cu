@@ -63,7 +63,6 @@ const Env &env()
         v.mlp_no_pair_tiles = on("FFB6D_MLP_NO_MT2");
         v.check_indices = on("FFB6D_CHECK_INDICES");
         v.grid_thread_search = on("FFB6D_GRID_THREAD_SEARCH");
-        v.knn_max_ctas = getenv("FFB6D_KNN_MAX_CTAS") ? atoi(getenv("FFB6D_KNN_MAX_CTAS")) : 0;
         const char *x;
         v.grid_scale = (x = getenv("FFB6D_GRID_SCALE")) ? (float)atof(x) : 1.0f;
         v.grid_scale_k1 = (x = getenv("FFB6D_GRID_SCALE_K1")) ? (float)atof(x) : 2.5f;

@@ -82,8 +82,6 @@ struct Env {
     bool mlp_no_pair_tiles; // FFB6D_MLP_NO_MT2=1: one 128-row weight tile per CTA for every layer (A/B timing)
     bool check_indices;     // FFB6D_CHECK_INDICES=1: validate gather indices (synchronises; debugging aid)
     bool grid_thread_search;
-    int knn_max_ctas;       // FFB6D_KNN_MAX_CTAS=n: cap the search kernels at n CTAs per SM (leaves registers and warp
-                            // slots to the HBM-bound gathers that run concurrently); 0 = no cap
     float grid_scale, grid_scale_k1;
     int grid_quantile;
 };

@@ -1425,32 +1425,20 @@ static int launch_search(const float *support, const float *query, int64_t B, in
     const bool self = (support == query) && (S == Q);
     const bool warp = K >= 2 && K <= 32 && !g_force_thread_search;
     FFB6D_CUDA(cudaMemsetAsync(qs.state, 0, (size_t)B * sizeof(QueryState), st));
-    // optional occupancy cap (experiment switch): unused dynamic shared memory sized so that at most n CTAs fit an SM
-    size_t cap_smem = 0;
-    if (env().knn_max_ctas > 0) {
-        cap_smem = (size_t)(228 * 1024) / (size_t)(env().knn_max_ctas + 1) + 1024;
-        if (cap_smem > (size_t)device_info().max_smem_optin - 20 * 1024) cap_smem = (size_t)device_info().max_smem_optin - 20 * 1024;
-        auto k_tile = grid_search_k1_tile_kernel<IdxT>;
-        auto k_gs = grid_search_group_kernel<IdxT, true, 16>;
-        auto k_gn = grid_search_group_kernel<IdxT, false, 16>;
-        FFB6D_OPTIN_SMEM(k_tile, device_info().max_smem_optin - 20 * 1024);
-        FFB6D_OPTIN_SMEM(k_gs, device_info().max_smem_optin - 1024);
-        FFB6D_OPTIN_SMEM(k_gn, device_info().max_smem_optin - 1024);
-    }
     const bool organised = K == 1 && !self && query_width >= 8 && Q % query_width == 0 && Q / query_width >= 4 &&
                            !g_force_thread_search;
     if (organised) {   // queries are an image: one warp per 8x4 pixel tile
         const int64_t tiles = ceil_div(query_width, 8) * ceil_div(Q / query_width, 4);
         dim3 tgrid((unsigned)ceil_div(tiles, 8), (unsigned)B);
-        grid_search_k1_tile_kernel<IdxT><<<tgrid, 256, cap_smem, st>>>(
+        grid_search_k1_tile_kernel<IdxT><<<tgrid, 256, 0, st>>>(
             query, (int)S, (int)Q, (int)query_width, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
     } else if (warp && K <= 16) {   // half a warp per query
         dim3 ggrid((unsigned)ceil_div(Q, 16), (unsigned)B);
         if (self)
-            grid_search_group_kernel<IdxT, true, 16><<<ggrid, 256, cap_smem, st>>>(
+            grid_search_group_kernel<IdxT, true, 16><<<ggrid, 256, 0, st>>>(
                 query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
         else
-            grid_search_group_kernel<IdxT, false, 16><<<ggrid, 256, cap_smem, st>>>(
+            grid_search_group_kernel<IdxT, false, 16><<<ggrid, 256, 0, st>>>(
                 query, (int)S, (int)Q, K, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
     } else if (warp) {
         dim3 wgrid((unsigned)ceil_div(Q, 8), (unsigned)B);

@@ -662,3 +662,67 @@ def grid_sub_sampling(points, features=None, labels=None, grid_size=0.1, verbose
     if cls is not None:
         out.append(sub_c[:m, :ldim].copy())      # wrapper.cpp:240-243: classes come back [M, ld]
     return out[0] if len(out) == 1 else tuple(out)
+
+
+def mean_shift_fit(votes, valid=None, bandwidth=0.05, max_iter=300, return_modes=False):
+    """Gaussian mean shift of ``G`` independent vote sets in one persistent kernel: the batched form of
+    ``MeanShiftTorch.fit`` (utils/meanshift_pytorch.py:33-57).
+
+    :param votes: ``[G,N,3]`` float32 CUDA.
+    :param valid: bool/uint8 mask of the points that vote, ``[N]`` (shared) or ``[G,N]``; ``None`` = all.
+    :return: ``(centres [G,3] f32, labels [G,N] bool, iters [G] int32)`` and, with ``return_modes``, the converged
+      position of every point ``[G,N,3]`` (the reference's ``ret_mid_res``)."""
+    _need_cuda(votes, "votes")
+    if votes.dim() != 3 or votes.shape[2] != 3 or votes.dtype != torch.float32:
+        raise ValueError("votes must be float32 [G,N,3]")
+    votes = votes.contiguous()
+    G, N, _ = votes.shape
+    dev = votes.device
+    stride = 0
+    vptr = None
+    if valid is not None:
+        _need_cuda(valid, "valid")
+        if valid.dtype == torch.bool:
+            valid = valid.to(torch.uint8)
+        if valid.dtype != torch.uint8:
+            raise ValueError("valid must be bool or uint8")
+        valid = valid.contiguous()
+        if tuple(valid.shape) == (N,):
+            stride = 0
+        elif tuple(valid.shape) == (G, N):
+            stride = N
+        else:
+            raise ValueError("valid must be [N] or [G,N]")
+        vptr = valid.data_ptr()
+    centres = torch.empty((G, 3), dtype=torch.float32, device=dev)
+    labels = torch.empty((G, N), dtype=torch.uint8, device=dev)
+    iters = torch.empty((G,), dtype=torch.int32, device=dev)
+    modes = torch.empty((G, N, 3), dtype=torch.float32, device=dev) if return_modes else None
+    with torch.cuda.device(dev):
+        nbytes = int(lib.ffb6d_mean_shift_workspace_bytes(G, N))
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=dev)
+        check(lib.ffb6d_mean_shift_fit(votes.data_ptr(), vptr, stride, G, N, float(bandwidth), int(max_iter),
+                                       centres.data_ptr(), labels.data_ptr(), iters.data_ptr(),
+                                       modes.data_ptr() if modes is not None else None, ws.data_ptr(), nbytes, _stream(dev)))
+    out = (centres, labels.bool(), iters)
+    return out + (modes,) if return_modes else out
+
+
+def best_fit_transform(A, B):
+    """Least-squares rigid transform of point sets ``A -> B`` (pvn3d_eval_utils_kpls.py:28-59), batched.
+
+    :param A, B: ``[G,M,3]`` (or ``[M,3]``) float32 CUDA; :return: ``[G,3,4]`` (or ``[3,4]``) float64 ``[R|t]``."""
+    _need_cuda(A, "A")
+    _need_cuda(B, "B")
+    single = A.dim() == 2
+    if single:
+        A, B = A[None], B[None]
+    if A.shape != B.shape or A.dim() != 3 or A.shape[2] != 3:
+        raise ValueError("A and B must both be [G,M,3]")
+    A = A.to(torch.float32).contiguous()
+    B = B.to(torch.float32).contiguous()
+    G, M, _ = A.shape
+    T = torch.empty((G, 3, 4), dtype=torch.float64, device=A.device)
+    with torch.cuda.device(A.device):
+        check(lib.ffb6d_best_fit_transform(A.data_ptr(), B.data_ptr(), G, M, T.data_ptr(), _stream(A.device)))
+    return T[0] if single else T

@@ -356,6 +356,35 @@ int ffb6d_sample_pixels(const float *depth, int64_t B, int64_t H, int64_t W, flo
                         uint64_t seed, int *choose, int *valid_count, void *workspace, size_t workspace_bytes,
                         ffb6d_stream_t stream);
 
+/* ---- keypoint voting and pose fitting (the step after the network) -------- */
+/*
+ * Gaussian mean shift of G independent vote sets, replacing MeanShiftTorch.fit
+ * (ffb6d/utils/meanshift_pytorch.py:28-57) as cal_frame_poses / cal_frame_poses_lm call it once per keypoint
+ * and once for the centre (ffb6d/utils/pvn3d_eval_utils_kpls.py:89-90, 124-137, 245-258).  One persistent
+ * kernel runs all G sets to convergence (max shift < bandwidth * 1e-3, or max_iter + 1 rounds, :30-47) without
+ * the N x N matrices and without a host round trip per iteration.
+ *   votes [G,N,3] f32; valid: u8 mask of the points that vote (the reference's votes[mask]), [N] shared by the
+ *   sets (valid_stride = 0), one row per set (valid_stride >= N elements between rows), or NULL (all vote)
+ *   -> centres [G,3] f32: the mode with the most modes within one bandwidth (lowest index on ties);
+ *      labels [G,N] u8: 1 where a point's mode lies within one bandwidth of it (0 for non-voting points);
+ *      iters [G] i32: rounds run; modes [G,N,3] f32 or NULL: every point's converged position
+ *      (`ret_mid_res=True`; rows of non-voting points are 0).
+ * A set without voting points gets centre (0,0,0) and 0 rounds.  Floating point: the sums run in another order
+ * than torch's, agreement is to about the stop threshold (tests/test_gpu_pose.py), not bitwise.
+ * G <= 64.  workspace: ffb6d_mean_shift_workspace_bytes(G, N) bytes.
+ */
+size_t ffb6d_mean_shift_workspace_bytes(int64_t G, int64_t N);
+int ffb6d_mean_shift_fit(const float *votes, const unsigned char *valid, int64_t valid_stride, int64_t G, int64_t N,
+                         float bandwidth, int max_iter, float *centres, unsigned char *labels, int *iters,
+                         float *modes, void *workspace, size_t workspace_bytes, ffb6d_stream_t stream);
+
+/*
+ * Least-squares rigid transform mapping point set A onto B (Kabsch / SVD), replacing best_fit_transform
+ * (ffb6d/utils/pvn3d_eval_utils_kpls.py:28-59), batched over G objects; float64 arithmetic like numpy's.
+ *   A, B [G,M,3] f32 (mesh keypoints, voted keypoints) -> T [G,3,4] f64 = [R | t], det R = +1.
+ */
+int ffb6d_best_fit_transform(const float *A, const float *B, int64_t G, int64_t M, double *T, ffb6d_stream_t stream);
+
 /* ---- grid subsampling --------------------------------------------------- */
 /*
  * Voxel-grid barycentre subsampling, replaces grid_subsampling()

@@ -163,3 +163,34 @@ def torch_functions():
         f2["relative_pos_encoding"] = lambda xyz, idx: rpe_raw(_Self(), xyz, idx)
         _torch_fns = dict(f1, **f2)
     return _torch_fns
+
+
+# ----------------------------------------------------------------------------- pose voting
+_pose_fns = None
+
+
+def pose_functions():
+    """{'MeanShiftTorch' (utils/meanshift_pytorch.py:27-57, the class itself), 'best_fit_transform'
+    (utils/pvn3d_eval_utils_kpls.py:28-59)} executed from the reference's own source text on the CPU.
+    (Importing pvn3d_eval_utils_kpls runs ``Config`` and reads dataset files; the function is taken out of the
+    file with ``ast`` instead.)"""
+    global _pose_fns
+    if _pose_fns is None:
+        if not reference_sources_present():
+            raise RuntimeError("reference sources not found under %s" % REF_ROOT)
+        import math
+        import torch
+        fns = {}
+        for path, names in ((os.path.join(REF_ROOT, "ffb6d", "utils", "meanshift_pytorch.py"),
+                             ("gaussian_kernel", "distance_batch", "MeanShiftTorch")),
+                            (os.path.join(REF_ROOT, "ffb6d", "utils", "pvn3d_eval_utils_kpls.py"), ("best_fit_transform",))):
+            with open(path) as fh:
+                tree = ast.parse(fh.read())
+            ns = {"torch": torch, "np": np, "math": math}
+            for node in tree.body:
+                if isinstance(node, (ast.FunctionDef, ast.ClassDef)) and node.name in names:
+                    exec(compile(ast.Module(body=[node], type_ignores=[]), path, "exec"), ns)
+            for n in names:
+                fns[n] = ns[n]
+        _pose_fns = fns
+    return _pose_fns

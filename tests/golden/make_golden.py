@@ -375,6 +375,57 @@ def train_cases():
     return cases
 
 
+def pose_vote_sets(seed, n, n_sets=3):
+    """Synthetic keypoint votes: a dense cluster around the true keypoint, a smaller decoy cluster and
+    uniform outliers (what per-point offset predictions look like on a partly mis-segmented object)."""
+    g = np.random.RandomState(seed)
+    sets = []
+    for s in range(n_sets):
+        centre = g.uniform(-0.2, 0.2, 3) + np.array([0.0, 0.0, 0.9])
+        n_main = int(n * 0.7)
+        n_decoy = int(n * 0.2)
+        main = centre + g.normal(0, 0.008 + 0.004 * s, (n_main, 3))
+        decoy = centre + np.array([0.09, -0.03, 0.02]) + g.normal(0, 0.01, (n_decoy, 3))
+        out = centre + g.uniform(-0.3, 0.3, (n - n_main - n_decoy, 3))
+        v = np.concatenate((main, decoy, out)).astype(np.float32)
+        sets.append(v[g.permutation(n)])
+    return np.stack(sets)
+
+
+def pose_cases():
+    """Outputs of the reference's MeanShiftTorch.fit / best_fit_transform (executed from its source on the CPU)."""
+    P = R.pose_functions()
+    out = {}
+    for name, seed, n, bw, max_iter in (("small", 0, 64, 0.04, 300), ("mid", 1, 700, 0.04, 300), ("wide", 2, 1500, 0.05, 300),
+                                        ("capped", 3, 400, 0.04, 5), ("single", 4, 1, 0.04, 300)):
+        votes = pose_vote_sets(seed, n)
+        out[name + "_votes"] = votes
+        out[name + "_params"] = np.array([bw, max_iter], np.float64)
+        ms = P["MeanShiftTorch"](bandwidth=bw, max_iter=max_iter)
+        ctrs, labs = [], []
+        for g in range(votes.shape[0]):
+            c, lab = ms.fit(torch.from_numpy(votes[g]))
+            ctrs.append(c.numpy())
+            labs.append(lab.numpy())
+        out[name + "_centres"] = np.stack(ctrs).astype(np.float32)
+        out[name + "_labels"] = np.stack(labs).astype(np.uint8)
+    g = np.random.RandomState(11)
+    A = g.uniform(-0.1, 0.1, (6, 9, 3))
+    Bs = []
+    for k in range(6):
+        q, _ = np.linalg.qr(g.normal(size=(3, 3)))
+        if np.linalg.det(q) < 0:
+            q[:, 0] *= -1
+        Bs.append(A[k] @ q.T + g.uniform(-0.5, 0.5, 3) + g.normal(0, 0.002, (9, 3)))
+    A[4, :, 2] = 0.0                                         # coplanar mesh keypoints
+    Bs[5] = Bs[5] * np.array([1.0, 1.0, -1.0])               # a mirrored target: the reflection branch
+    B = np.stack(Bs)
+    A32, B32 = A.astype(np.float32), B.astype(np.float32)
+    out["fit_A"], out["fit_B"] = A32, B32
+    out["fit_T"] = np.stack([P["best_fit_transform"](A32[k].astype(np.float64), B32[k].astype(np.float64)) for k in range(6)])
+    return out
+
+
 def main():
     if not R.reference_sources_present():
         raise SystemExit("needs /root/reference")
@@ -382,7 +433,7 @@ def main():
     if len(sys.argv) > 2 and sys.argv[1] == "--only":      # regenerate one fixture file
         which = sys.argv[2]
         fn = {"lfa": lfa_cases, "knn": knn_cases, "gather": gather_cases, "grid": grid_cases, "train": train_cases,
-              "fusion": fusion_cases}[which]
+              "fusion": fusion_cases, "pose": pose_cases}[which]
         np.savez_compressed(os.path.join(OUT, which + "_cases.npz"), **fn())
         print("rewrote", which + "_cases.npz")
         return
@@ -392,6 +443,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "lfa_cases.npz"), **lfa_cases())
     np.savez_compressed(os.path.join(OUT, "fusion_cases.npz"), **fusion_cases())
     np.savez_compressed(os.path.join(OUT, "train_cases.npz"), **train_cases())
+    np.savez_compressed(os.path.join(OUT, "pose_cases.npz"), **pose_cases())
     dig = {"generator": "ffb6d_b200.synthetic.make_frame", "frames": {}}
     for seed, n in ((0, 12288), (1, 12288), (2, 3072)):
         dig["frames"]["seed%d_n%d" % (seed, n)] = {"seed": seed, "n_points": n,
