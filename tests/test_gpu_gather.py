@@ -92,6 +92,26 @@ def test_schedule_shapes_vs_oracle(cuda, case):
     assert np.array_equal(got_cl.cpu().numpy(), want)
 
 
+@pytest.mark.parametrize("shape", [(5, 64, 19200, 3072, 16), (3, 64, 12288, 3072, 16), (2, 128, 4800, 2500, 16),
+                                   (3, 96, 3072, 1500, 8), (1, 160, 768, 192, 16), (7, 33, 1000, 1025, 16)],
+                         ids=lambda s: "B%d-C%d-S%d-Q%d-K%d" % s)
+def test_random_sample_large_shapes(cuda, shape):
+    """Max-pool gathers at batch sizes where B*C exceeds the SM count (every dispatch branch of launch_ncs at
+    more than one frame), odd channel counts, a partial last query group, NaN / -inf rows, last-element indices."""
+    B, C, S, Q, K = shape
+    g = torch.Generator().manual_seed(B * 1000 + C)
+    feat = torch.randn(B, C, S, 1, generator=g)
+    feat[B - 1, C // 2, ::97] = float("nan")
+    feat[0, 1, :] = float("-inf")
+    idx = torch.randint(0, S, (B, Q, K), generator=g, dtype=torch.int64)
+    idx[:, 0, :] = S - 1                                           # the last element of a row
+    want = O.random_sample(feat.numpy(), idx.numpy())
+    for ii in (idx.cuda(), idx.cuda().int()):
+        got = F.random_sample(feat.cuda(), ii).cpu().numpy()
+        assert np.array_equal(np.isnan(got), np.isnan(want))
+        assert np.array_equal(got[~np.isnan(got)], want[~np.isnan(want)])
+
+
 def test_nan_and_inf_propagate_like_torch_max(cuda):
     feat = torch.randn(1, 4, 20, 1)
     feat[0, 0, 3] = float("nan")
