@@ -51,6 +51,15 @@ __device__ __forceinline__ void grid_sync(unsigned *counter, unsigned &target)
 
 __device__ __forceinline__ float4 ldcg4(const float4 *p) { return __ldcg(p); }
 
+// 2^x on the SFU without exp2f's denormal-range fix-up (3 extra instructions per call): weights below 2^-126 flush
+// to zero, and a weight of 1e-38 against the point's own weight of 1 is below fp32 resolution anyway
+__device__ __forceinline__ float ex2_ftz(float x)
+{
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 // MODE 0: one mean-shift update of the item's points; MODE 1: neighbours within the bandwidth
 template <int MODE>
 __device__ __forceinline__ void ms_item(const float4 *__restrict__ cur, float4 *__restrict__ nxt, int n, int tile,
@@ -75,7 +84,7 @@ __device__ __forceinline__ void ms_item(const float4 *__restrict__ cur, float4 *
             dx = p1.x - c.x, dy = p1.y - c.y, dz = p1.z - c.z;
             const float d1 = fmaf(dz, dz, fmaf(dy, dy, dx * dx));
             if (MODE == 0) {
-                const float w0 = exp2f(d0 * neg_scale), w1 = exp2f(d1 * neg_scale);
+                const float w0 = ex2_ftz(d0 * neg_scale), w1 = ex2_ftz(d1 * neg_scale);
                 a0x = fmaf(w0, c.x, a0x), a0y = fmaf(w0, c.y, a0y), a0z = fmaf(w0, c.z, a0z), a0w += w0;
                 a1x = fmaf(w1, c.x, a1x), a1y = fmaf(w1, c.y, a1y), a1z = fmaf(w1, c.z, a1z), a1w += w1;
             } else {

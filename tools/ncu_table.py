@@ -31,7 +31,10 @@ for n, r in enumerate(rows[2:]):
             vals.append("")
             continue
         v = float(r[idx[key]].replace(",", ""))
-        if mul is None:     # bytes with a unit column
+        if key == "gpu__time_duration.sum":     # ncu scales the unit per report: normalise to microseconds
+            v *= {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3, "s": 1e6, "second": 1e6}.get(units[idx[key]], 1.0)
+            vals.append("%.1f" % v)
+        elif mul is None:     # bytes with a unit column
             u = units[idx[key]]
             v *= {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1.0)
             vals.append("%.2f" % v)
