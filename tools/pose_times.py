@@ -57,7 +57,7 @@ for N in (1024, 4096, 12288):
         t_torch = timed(lambda: [torch_mean_shift(v[g]) for g in range(9)], n=1)
         ct = torch.stack([torch_mean_shift(v[g])[0] for g in range(9)])
         err = (ct - c).abs().max().item()
-    pairs = 9.0 * N * N * float(it.max().item())
+    pairs = float(N) * N * float(it.sum().item())        # sets stop at different rounds
     print("N=%5d: ours %.3f ms (%d rounds, %.1f Gpair/s)%s" % (
         N, t_ours, it.max().item(), pairs / t_ours / 1e6,
         "" if t_torch is None else " | torch ops %.1f ms (%.0fx) max |dcentre| %.2e" % (t_torch, t_torch / t_ours, err)), flush=True)
