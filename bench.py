@@ -557,6 +557,8 @@ def main():
         entry = {"share": v["ms"] / tot_ms, "ms_per_step": v["ms"] / steps}
         if k == K1_FAMILY:
             entry["queries_per_step"] = n_q["k1"]
+            entry["note"] = ("queries ANSWERED per step; 3 of the 11 searches (p2r_ds_nei_idx0/1/2) are strided pixel subsets of "
+                             "p2r_up_nei_idx2/1/0 (image level 2s is every other pixel of level s): copied, not run")
         elif k == SELF_FAMILY:
             entry["queries_per_step"] = n_q["k16_self"]
         elif k == NONSELF_FAMILY:

@@ -59,6 +59,23 @@ static Sizes make_sizes(int64_t N0, int64_t H, int64_t W)
 
 static int64_t size_of(const Sizes &z, int kind, int id) { return kind == 0 ? z.cld[id] : z.img[id]; }
 
+// rows of a search from image level sr_c = every f-th pixel of every f-th image row of the search from level sr_c / f
+// (4-byte words: `words` per index row)
+__global__ void __launch_bounds__(256)
+strided_pixels_copy_kernel(const unsigned *__restrict__ in, unsigned *__restrict__ out, int Hc, int Wc, int Hp, int Wp, int f,
+                           int words, long long total)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= total) return;
+    const int wd = (int)(t % words);
+    long long px = t / words;
+    const int c = (int)(px % Wc);
+    px /= Wc;
+    const int r = (int)(px % Hc);
+    const long long b = px / Hc;
+    out[t] = __ldg(in + (((b * Hp + (long long)r * f) * Wp + (long long)c * f) * words + wd));
+}
+
 struct Plan {
     size_t levels_off[5];   // contiguous copies of cld levels 1..4
     size_t grid_off, scratch_off, total;
@@ -146,6 +163,21 @@ extern "C" int ffb6d_build_indices(const float *cld, const float *img2, const fl
                 (parent[i] < 0 || calls[j].qry_id < calls[parent[i]].qry_id))
                 parent[i] = j;
     }
+    // Image level sr_c is every (sr_c / sr_p)-th pixel of every (sr_c / sr_p)-th row of level sr_p: K = 1 searches from
+    // img4 / img8 into a cloud level are strided subsets of the search from img2 / img4 into the same level
+    // (p2r_ds_nei_idx0 of p2r_up_nei_idx2, idx1 of p2r_up_nei_idx1, idx2 of p2r_up_nei_idx0): copied, not searched.
+    int stride_f[22];
+    for (int i = 0; i < 22; ++i) {
+        stride_f[i] = 0;
+        if (calls[i].qry_kind != 1 || H % calls[i].qry_id != 0 || W % calls[i].qry_id != 0) continue;
+        for (int j = 0; j < 22; ++j)
+            if (j != i && calls[j].qry_kind == 1 && calls[j].sup_kind == calls[i].sup_kind && calls[j].sup_id == calls[i].sup_id &&
+                calls[j].K == calls[i].K && calls[j].qry_id < calls[i].qry_id && calls[i].qry_id % calls[j].qry_id == 0 &&
+                (parent[i] < 0 || calls[j].qry_id < calls[parent[i]].qry_id)) {
+                parent[i] = j;
+                stride_f[i] = calls[i].qry_id / calls[j].qry_id;
+            }
+    }
     void *grid = ws + plan.grid_off, *scratch = ws + plan.scratch_off;
     for (int i = 0; i < 22; ++i) {
         if (done[i]) continue;
@@ -182,6 +214,15 @@ extern "C" int ffb6d_build_indices(const float *cld, const float *img2, const fl
         if (parent[i] < 0) continue;
         const int64_t Qc = size_of(z, calls[i].qry_kind, calls[i].qry_id), Qp = size_of(z, calls[parent[i]].qry_kind, calls[parent[i]].qry_id);
         const size_t row = (size_t)calls[i].K * esz;
+        if (stride_f[i] > 0) {
+            const int sc = calls[i].qry_id, sp = calls[parent[i]].qry_id, words = (int)(row / 4);
+            const long long total = (long long)B * Qc * words;
+            strided_pixels_copy_kernel<<<(unsigned)ceil_div(total, 256), 256, 0, st>>>(
+                (const unsigned *)out[parent[i]], (unsigned *)out[i], (int)(H / sc), (int)(W / sc), (int)(H / sp), (int)(W / sp),
+                stride_f[i], words, total);
+            FFB6D_LAUNCH_OK("strided_pixels_copy_kernel");
+            continue;
+        }
         FFB6D_CUDA(cudaMemcpy2DAsync(out[i], (size_t)Qc * row, out[parent[i]], (size_t)Qp * row, (size_t)Qc * row, (size_t)B,
                                      cudaMemcpyDeviceToDevice, st));
     }

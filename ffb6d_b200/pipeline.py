@@ -56,6 +56,7 @@ class FusionPass:
         import os
         unlocked = {}
         derived = S.derived_searches(S.knn_schedule(n_points, h, w, k))   # row slices of another search
+        derived.update({c: p_ for c, (p_, f_) in S.derived_image_searches(S.knn_schedule(n_points, h, w, k), h, w).items()})
         for op, key, C, Sz, Q, K in self.gathers:
             src = key.replace("cld_sub_idx", "cld_nei_idx")
             src = derived.get(src, src)

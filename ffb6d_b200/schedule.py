@@ -15,7 +15,7 @@ from .ops import knn_search, KnnGrid, knn_uses_grid
 
 from .tables import (RGB_DS_SR, RGB_UP_SR, PCLD_SUB_S_R, N_DS_LAYERS, N_UP_LAYERS, K_NEIGH,  # noqa: F401
                      DS_RGB_OC, DS_RNDLA_OC, UP_RGB_OC, UP_RNDLA_OC, knn_schedule, set_size, gather_schedule,
-                     fusion_mlp_schedule, knn_alg_bytes, gather_alg_bytes, frame_alg_bytes, derived_searches)
+                     fusion_mlp_schedule, knn_alg_bytes, gather_alg_bytes, frame_alg_bytes, derived_searches, derived_image_searches)
 
 
 def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
@@ -117,6 +117,14 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     children = {}
     for child, parent in derived.items():
         children.setdefault(parent, []).append(child)
+    # Image level sr_c is every f-th pixel of every f-th row of level sr_p = sr_c / f (stride slicing of the same
+    # organised cloud): a K = 1 search from img4 / img8 into a cloud level is a strided subset of the search from
+    # img2 / img4 into the same level (p2r_ds_nei_idx0 of p2r_up_nei_idx2, idx1 of p2r_up_nei_idx1, idx2 of
+    # p2r_up_nei_idx0): three more searches that are copied instead of run.
+    derived_img = derived_image_searches(calls, H, W)
+    children_img = {}
+    for child, (parent, f) in derived_img.items():
+        children_img.setdefault(parent, []).append((child, f))
 
     fork()
     # a search waits only for ITS grid, a consumer only for ITS index tensor (events, not joins)
@@ -140,7 +148,7 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             if par:
                 built[g] = torch.cuda.Event()
                 built[g].record()
-    order = [c for c in order if c[0] not in derived]
+    order = [c for c in order if c[0] not in derived and c[0] not in derived_img]
     qsize = {key: sets[q].shape[1] for key, s, q, kk in calls}
     for i, (key, s, q, kk) in enumerate(order):
         sup, qry = sets[s], sets[q]
@@ -165,6 +173,10 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
                 done.append("cld_sub_idx%d" % lvl)
             for child in children.get(key, ()):   # prefix slices instead of separate searches (see above)
                 inputs[child] = inputs[key][:, :qsize[child], :].contiguous()
+                done.append(child)
+            for child, f in children_img.get(key, ()):   # strided pixel subsets (see above)
+                hp, wp = H // q[1], W // q[1]
+                inputs[child] = inputs[key].view(B, hp, wp, kk)[:, ::f, ::f, :].reshape(B, -1, kk)
                 done.append(child)
             if par and events is not None:
                 ev = torch.cuda.Event()

@@ -60,6 +60,26 @@ def derived_searches(calls):
     return derived
 
 
+def derived_image_searches(calls, h=480, w=640):
+    """``{child key: (parent key, f)}``: searches whose QUERIES are an image level that is a strided subset of a
+    finer level searched against the same support with the same K.  The stride-``sr`` pyramid level is
+    ``dpt_xyz[::sr, ::sr]`` (ycb_dataset.py:253-264), so level ``sr_c`` is every ``f = sr_c / sr_p``-th pixel of every
+    ``f``-th row of level ``sr_p``: ``p2r_ds_nei_idx0`` (cld1 <- img4) is that subset of ``p2r_up_nei_idx2``
+    (cld1 <- img2), ``p2r_ds_nei_idx1`` (cld2 <- img8) of ``p2r_up_nei_idx1`` (cld2 <- img2), ``p2r_ds_nei_idx2``
+    (cld3 <- img8) of ``p2r_up_nei_idx0`` (cld3 <- img4).  Only when the image size is a multiple of ``sr_c``."""
+    by_group, derived = {}, {}
+    for key, s, q, kk in calls:
+        if q[0] == "img":
+            by_group.setdefault((s, kk), []).append((q[1], key))
+    for members in by_group.values():
+        members.sort()
+        sr_p, parent = members[0]
+        for sr_c, key in members[1:]:
+            if sr_c > sr_p and sr_c % sr_p == 0 and h % sr_c == 0 and w % sr_c == 0:
+                derived[key] = (parent, sr_c // sr_p)
+    return derived
+
+
 def set_size(name, n_points=12288, h=480, w=640):
     kind, a = name
     if kind == "cld":
