@@ -138,3 +138,54 @@ def test_index_validation(cuda):
     out = F.random_sample(feat, idx)
     out.sum().backward()
     assert torch.isfinite(feat.grad).all()
+
+
+def test_wrap_padded_frame_downstream_features_unchanged(cuda):
+    """The datasets pad frames with fewer valid pixels than points by repeating pixels (np.pad 'wrap',
+    ycb_dataset.py:230): the cloud then holds duplicated points and KNN has exact distance ties, where our neighbour
+    order (ascending index) differs from the reference's (KD-tree traversal order).  Duplicated points carry identical
+    features (same pixel, same network input), so every gather of the forward pass must still produce the reference's
+    values: checked with features that are functions of the point coordinates, the reference's KNN (oracle) on one side
+    and our index build on the other."""
+    import ffb6d_b200 as F
+    from ffb6d_b200.schedule import gather_schedule, knn_schedule
+    from ffb6d_b200.synthetic import image_pyramid_np, make_frame
+    n = 3072
+    fr = make_frame(11, n_points=n)
+    rs = np.random.RandomState(5)
+    keep = fr["choose"][0][: n * 5 // 8]
+    choose = np.pad(keep, (0, n - len(keep)), "wrap")
+    choose = choose[rs.permutation(n)]
+    cld = fr["dpt_xyz"].reshape(-1, 3)[choose]
+    assert len(np.unique(choose)) < n                                    # duplicated points exist
+    sets = {("cld", i): cld[: n // 4 ** i] for i in range(5)}
+    for sr, pts in image_pyramid_np(fr["dpt_xyz"]).items():
+        sets[("img", sr)] = pts
+    ours = F.build_ffb6d_indices(torch.from_numpy(cld)[None].cuda(), torch.from_numpy(fr["dpt_xyz"])[None].cuda())
+    ref = {key: O.knn_search(sets[s][None], sets[q][None], kk) for key, s, q, kk in knn_schedule(n)}
+    ref.update({"cld_sub_idx%d" % i: ref["cld_nei_idx%d" % i][:, : n // 4 ** (i + 1)] for i in range(4)})
+    n_tied = 0
+    for key, s, q, kk in knn_schedule(n):
+        got = ours[key].cpu().numpy()
+        ok, _, _, msg = O.knn_matches(sets[s][None], sets[q][None], got, ref[key])
+        assert ok, (key, msg)
+        n_tied += int((got != ref[key]).any(axis=2).sum())
+    assert n_tied > 0                                                    # the tie order really differs somewhere
+    calls = {key: (s, q) for key, s, q, kk in knn_schedule(n)}
+    for op, key, C, S, Q, K in gather_schedule(n):
+        if op == "choose":
+            continue
+        base = key.replace("cld_sub_idx", "cld_nei_idx")
+        pts = sets[calls[base][0]]                                       # the gather reads features of the SUPPORT set
+        assert pts.shape[0] == S
+        cc = min(C, 24)
+        w = rs.normal(size=(cc, 3)).astype(np.float32)
+        feat = np.sin(pts @ w.T * 7.0).T[None, :, :, None].astype(np.float32).copy()      # [1,cc,S,1], a function of xyz
+        idx_ours = ours[key]
+        if op == "random_sample":
+            got = F.random_sample(torch.from_numpy(feat).cuda(), idx_ours).cpu().numpy()
+            want = O.random_sample(feat, ref[key].astype(np.int64))
+        else:
+            got = F.nearest_interpolation(torch.from_numpy(feat).cuda(), idx_ours).cpu().numpy()
+            want = O.nearest_interpolation(feat, ref[key].astype(np.int64))
+        assert np.array_equal(got, want), key
