@@ -73,3 +73,38 @@ def test_grid_random():
     o1 = np.lexsort((rp[:, 2], rp[:, 1], rp[:, 0]))
     o2 = np.lexsort((op[:, 2], op[:, 1], op[:, 0]))
     assert np.array_equal(rp[o1], op[o2]) and np.array_equal(rf[o1], of[o2])
+
+
+def test_wrap_padded_frame_tie_order_differs_but_gathers_agree():
+    """A frame padded with repeated pixels (np.pad 'wrap', ycb_dataset.py:230): thousands of index rows differ
+    between the reference's KD-tree order and the (distance, index) order -- within the tie contract -- yet every
+    gather of the forward pass returns the same values, because tied points are duplicates with identical features."""
+    from conftest import frame_point_sets
+    from ffb6d_b200.synthetic import make_frame
+    from ffb6d_b200.tables import gather_schedule, knn_schedule
+    n = 3072
+    fr = make_frame(11, n_points=n)
+    rs = np.random.RandomState(5)
+    keep = fr["choose"][0][: n * 5 // 8]
+    choose = np.pad(keep, (0, n - len(keep)), "wrap")[rs.permutation(n)]
+    fr = dict(fr, cld=fr["dpt_xyz"].reshape(-1, 3)[choose])
+    sets = frame_point_sets(fr, n)
+    ref, ours, differing = {}, {}, 0
+    for key, s, q, kk in knn_schedule(n):
+        ref[key] = R.knn_search(sets[s][None], sets[q][None], kk)
+        ours[key] = O.knn_search(sets[s][None], sets[q][None], kk)
+        ok, _, _, msg = O.knn_matches(sets[s][None], sets[q][None], ours[key], ref[key])
+        assert ok, (key, msg)
+        differing += int((ref[key] != ours[key]).any(axis=2).sum())
+    assert differing > 1000
+    for d in (ref, ours):
+        d.update({"cld_sub_idx%d" % i: d["cld_nei_idx%d" % i][:, : n // 4 ** (i + 1)] for i in range(4)})
+    support_of = {key: s for key, s, q, kk in knn_schedule(n)}
+    for op, key, C, S, Q, K in gather_schedule(n):
+        if op == "choose":
+            continue
+        pts = sets[support_of[key.replace("cld_sub_idx", "cld_nei_idx")]]
+        w = rs.normal(size=(min(C, 16), 3)).astype(np.float32)
+        feat = np.sin(pts @ w.T * 7.0).T[None, :, :, None].astype(np.float32).copy()     # features = f(xyz)
+        f = O.random_sample if op == "random_sample" else O.nearest_interpolation
+        assert np.array_equal(f(feat, ref[key].astype(np.int64)), f(feat, ours[key].astype(np.int64))), key
