@@ -219,6 +219,7 @@ mean_shift_kernel(const float *__restrict__ votes, const unsigned char *__restri
     }
 
     // ---- phase C: the mode with the most modes within one bandwidth (first index on ties) ----
+    __syncthreads();   // the `break` above leaves the loop right after reading s_first[G]: order that read before the rewrite
     if (t == 0) {
         int acc = 0;
         for (int g = 0; g < G; ++g) s_first[g] = acc, acc += (s_n[g] + MS_IT - 1) / MS_IT;
