@@ -63,6 +63,11 @@ const Env &env()
         v.mlp_no_pair_tiles = on("FFB6D_MLP_NO_MT2");
         v.check_indices = on("FFB6D_CHECK_INDICES");
         v.grid_thread_search = on("FFB6D_GRID_THREAD_SEARCH");
+        v.k1_tile_old = on("FFB6D_K1_TILE_OLD");
+        v.k1_tile_warps = getenv("FFB6D_K1_TILE_WARPS") ? atoi(getenv("FFB6D_K1_TILE_WARPS")) : 8;
+        v.gather_noalloc = on("FFB6D_GATHER_NOALLOC");
+        v.gather_smem_pad = getenv("FFB6D_GATHER_SMEM_PAD") ? atoi(getenv("FFB6D_GATHER_SMEM_PAD")) : 0;
+        if (v.gather_smem_pad < 0 || v.gather_smem_pad > 47 * 1024) v.gather_smem_pad = 0;
         const char *x;
         v.grid_scale = (x = getenv("FFB6D_GRID_SCALE")) ? (float)atof(x) : 1.0f;
         v.grid_scale_k1 = (x = getenv("FFB6D_GRID_SCALE_K1")) ? (float)atof(x) : 2.5f;

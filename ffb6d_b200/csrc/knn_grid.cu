@@ -887,6 +887,210 @@ __device__ __forceinline__ void warp_list_offer(key_t64 &mine, key_t64 cand, int
     }
 }
 
+// Far queries of an ORGANISED K = 1 search (the hole pixels of an image level: ~10 % of the queries, all at the
+// origin).  register_overflow() costs every tile a same-address atomicAdd on the item's dup counter -- 2400 warps
+// per frame queue on one L2 atomic unit, half of the tile kernel's stall samples (ncu source page) -- and leaves the
+// copies to the last CTA of the overflow pass.  Here a far query that equals the item's representative only writes
+// the sentinel -1 into its result slot (no atomic, no list); grid_far_fill_kernel replaces the sentinels with the
+// representative's answer after the overflow pass.  The representative itself and far queries that differ from it
+// (rare) take the list path as before.
+template <typename IdxT>
+__device__ __forceinline__ void register_far_k1(const float *__restrict__ query, int Q, int b, int q, float qx, float qy,
+                                                float qz, QueryState *state_all, int *__restrict__ ovf_all,
+                                                IdxT *__restrict__ idx_out)
+{
+    QueryState *Pw = state_all + b;
+    int rep = *(volatile int *)&Pw->rep_q;            // stored as q+1 so that all-zero means 'none'
+    if (rep == 0) rep = atomicCAS(&Pw->rep_q, 0, q + 1);
+    rep -= 1;
+    bool dup = false;
+    if (rep != -1 && rep != q) {
+        const float *rp = query + ((size_t)b * Q + rep) * 3;
+        dup = (__ldg(rp) == qx) && (__ldg(rp + 1) == qy) && (__ldg(rp + 2) == qz);
+    }
+    if (dup) {
+        idx_out[(size_t)b * Q + q] = (IdxT)-1;
+    } else {
+        auto g = cooperative_groups::coalesced_threads();
+        int base = 0;
+        if (g.thread_rank() == 0) base = atomicAdd(&Pw->ovf_count, (int)g.size());
+        const int slot = g.shfl(base, 0) + (int)g.thread_rank();
+        ovf_all[(size_t)b * Q + slot] = q;
+    }
+}
+
+// after the overflow pass: every sentinel of an item becomes the representative's (now final) answer
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+grid_far_fill_kernel(int Q, const QueryState *__restrict__ state_all, IdxT *__restrict__ idx_out)
+{
+    const int b = blockIdx.y;
+    const int rep = state_all[b].rep_q - 1;
+    if (rep < 0) return;
+    IdxT *o = idx_out + (size_t)b * Q;
+    const IdxT v = o[rep];
+    for (int q = blockIdx.x * blockDim.x + threadIdx.x; q < Q; q += gridDim.x * blockDim.x)
+        if (o[q] == (IdxT)-1) o[q] = v;
+}
+
+// ------------------------------------------------------------------ E0'. the same tile search, lean issue path
+// grid_search_k1_tile_kernel spends two thirds of its ~1300 warp instructions per tile outside the distance
+// arithmetic (SASS: 93 instructions per 4 candidates in the walk, a third of them uniform-datapath bound checks;
+// 190 for a staging round that always runs four binary-search sub-batches; integer divisions in the prologue).
+// This version keeps the algorithm and the certificate and removes that overhead:
+//   * the staged list is padded to a multiple of four with sentinel candidates at +inf (their key sorts after
+//     every real candidate), so the walk has no per-candidate bound checks and its LDS.128 use immediate offsets;
+//   * best-so-far is ONE 64-bit key (distance bits << 32 | index): the total order is a single unsigned compare;
+//   * staging runs only as many 32-candidate sub-batches as there are candidates;
+//   * tile and row coordinates come from exact float reciprocals instead of integer divisions (host passes the
+//     tile counts; (i + 0.5) * (1 / n) truncates to i / n whenever i < 2^22, guaranteed by the launcher).
+template <typename IdxT, int NW>
+__global__ void __launch_bounds__(NW * 32, 1024 / (NW * 32))
+grid_search_k1_tile2_kernel(const float *__restrict__ query, int S, int Q, int qw, int qh, int tiles_x, int n_tiles,
+                            const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
+                            size_t cursor_stride, const float4 *__restrict__ sorted_all,
+                            IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
+{
+    constexpr int TW = 8, TH = 4;               // tile = 8 x 4 pixels
+    constexpr int MAX_ROWS = 32, MAX_X = 8;     // widest shared box: 32 cell rows of up to 8 cells
+    constexpr int TILE_CAND = 128;              // candidates staged per round and warp
+    __shared__ float4 s_cand[NW][TILE_CAND];
+    __shared__ int s_list[NW * 32];
+    __shared__ int s_count;
+    const unsigned FULL = 0xffffffffu;
+    const int b = blockIdx.y;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int tile = blockIdx.x * NW + wid;
+    const GridParams Ps = params_all[b];
+    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
+    const float4 *sorted = sorted_all + (size_t)b * S;
+    const float INF = __int_as_float(0x7f800000);
+    if (threadIdx.x == 0) s_count = 0;
+    if (NW > 1) __syncthreads();
+    else __syncwarp();
+
+    const int trow = (int)(((float)tile + 0.5f) * (1.0f / (float)tiles_x));   // == tile / tiles_x (see above)
+    const int px = (tile - trow * tiles_x) * TW + (lane & (TW - 1)), py = trow * TH + (lane >> 3);
+    const bool inimg = tile < n_tiles && px < qw && py < qh;
+    const int q = inimg ? py * qw + px : 0;
+    float qx = 0.f, qy = 0.f, qz = 0.f;
+    if (inimg) {
+        const float *qp = query + ((size_t)b * Q + q) * 3;
+        qx = __ldg(qp);
+        qy = __ldg(qp + 1);
+        qz = __ldg(qp + 2);
+    }
+    const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
+    const float h = Ps.h, slack = Ps.slack;
+    const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
+                            fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
+    // state: 0 answered, 1 finish with the ring search, 2 overflow (far from the support), 3 no query
+    int state = !inimg ? 3 : ((out > (float)RMAX * h || !(qx == qx && qy == qy && qz == qz)) ? 2 : 1);
+    const bool part = state == 1;
+    const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
+    const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
+    const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
+    const int big = 0x3fffffff;
+    int X0 = __reduce_min_sync(FULL, part ? cx : big), X1 = __reduce_max_sync(FULL, part ? cx : -1);
+    int Y0 = __reduce_min_sync(FULL, part ? cy : big), Y1 = __reduce_max_sync(FULL, part ? cy : -1);
+    int Z0 = __reduce_min_sync(FULL, part ? cz : big), Z1 = __reduce_max_sync(FULL, part ? cz : -1);
+    if (X1 >= 0) {   // warp-uniform: somebody takes part
+        X0 = max(X0 - 1, 0); X1 = min(X1 + 1, nx - 1);
+        Y0 = max(Y0 - 1, 0); Y1 = min(Y1 + 1, ny - 1);
+        Z0 = max(Z0 - 1, 0); Z1 = min(Z1 + 1, nz - 1);
+        const int by = Y1 - Y0 + 1, nrows = by * (Z1 - Z0 + 1);
+        if (nrows <= MAX_ROWS && X1 - X0 + 1 <= MAX_X) {
+            int beg = 0, end = 0;
+            if (lane < nrows) {   // lane r looks up cell row r of the box
+                const int rz = (int)(((float)lane + 0.5f) * (1.0f / (float)by));   // == lane / by (lane, by <= 32)
+                const int row = ((Z0 + rz) * ny + (Y0 + lane - rz * by)) * nx;
+                beg = (row + X0 > 0) ? __ldg(cell_end + row + X0 - 1) : 0;
+                end = __ldg(cell_end + row + X1);
+            }
+            const int cnt = end - beg;
+            int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int u = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += u;
+            }
+            const int total = __shfl_sync(FULL, incl, 31);
+            const int excl = incl - cnt;
+            float4 *stage = s_cand[wid];
+            key_t64 best = KEY_EMPTY;   // (+inf, 0)
+            for (int c0 = 0; c0 < total; c0 += TILE_CAND) {
+                const int n = min(TILE_CAND, total - c0);
+                const int n4 = (n + 3) & ~3;
+                __syncwarp();
+                for (int u0 = 0; u0 < n4; u0 += 32) {   // warp-uniform trip count
+                    const int j = c0 + u0 + lane;
+                    int seg = 0;   // number of rows whose inclusive count is <= j
+#pragma unroll
+                    for (int step = 16; step > 0; step >>= 1) {
+                        const int v = __shfl_sync(FULL, incl, seg + step - 1);
+                        if (v <= j) seg += step;
+                    }
+                    const int sb = __shfl_sync(FULL, beg, seg & 31), se = __shfl_sync(FULL, excl, seg & 31);
+                    float4 c = make_float4(INF, INF, INF, __int_as_float(0x7fffffff));   // sentinel: sorts last
+                    if (j < total) c = __ldg(sorted + sb + (j - se));
+                    if (u0 + lane < n4) stage[u0 + lane] = c;
+                }
+                __syncwarp();
+                for (int p = 0; p < n4; p += 4) {
+                    float4 c[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) c[u] = stage[p + u];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const key_t64 k = make_key(ref_sqdist(qx, qy, qz, c[u].x, c[u].y, c[u].z), __float_as_int(c[u].w));
+                        best = k < best ? k : best;
+                    }
+                }
+            }
+            if (part) {
+                const float bd = key_dist(best);
+                // distance to the nearest face of the box that still has cells behind it
+                float m = INF;
+                if (X0 > 0) m = fminf(m, qx - (Ps.lo[0] + (float)X0 * h));
+                if (X1 < nx - 1) m = fminf(m, (Ps.lo[0] + (float)(X1 + 1) * h) - qx);
+                if (Y0 > 0) m = fminf(m, qy - (Ps.lo[1] + (float)Y0 * h));
+                if (Y1 < ny - 1) m = fminf(m, (Ps.lo[1] + (float)(Y1 + 1) * h) - qy);
+                if (Z0 > 0) m = fminf(m, qz - (Ps.lo[2] + (float)Z0 * h));
+                if (Z1 < nz - 1) m = fminf(m, (Ps.lo[2] + (float)(Z1 + 1) * h) - qz);
+                const float ms = m - slack;
+                const bool ok = (m == INF) ? (bd < INF || S == 0) : (ms > 0.f && bd <= ms * ms * (1.0f - 1e-5f));
+                if (ok) {
+                    idx_out[(size_t)b * Q + q] = (IdxT)(unsigned)(best & 0xffffffffu);
+                    state = 0;
+                }
+            }
+        }
+    }
+    // ---- the uncertified queries of the CTA, compacted, finished by the per-thread ring search
+    if (state == 1) s_list[atomicAdd(&s_count, 1)] = q;
+    if (NW > 1) __syncthreads();   // a CTA of one warp holds no other warp back while a lane finishes its ring search
+    else __syncwarp();
+    const int n_retry = s_count;
+    int q2 = -1;
+    float rx = 0.f, ry = 0.f, rz = 0.f;
+    bool retry_failed = false;
+    if ((int)threadIdx.x < n_retry) {
+        q2 = s_list[threadIdx.x];
+        const float *qp = query + ((size_t)b * Q + q2) * 3;
+        rx = __ldg(qp);
+        ry = __ldg(qp + 1);
+        rz = __ldg(qp + 2);
+        TopK<1> top;
+        top.init();
+        if (thread_search<1>(rx, ry, rz, 1, Ps, cell_end, sorted, top))
+            idx_out[(size_t)b * Q + q2] = (IdxT)top.i[0];
+        else
+            retry_failed = true;
+    }
+    if (retry_failed) register_overflow(query, Q, b, q2, rx, ry, rz, state_all, ovf_all);
+    if (state == 2) register_far_k1<IdxT>(query, Q, b, q, qx, qy, qz, state_all, ovf_all, idx_out);
+}
+
 template <typename IdxT, bool SELF>
 __global__ void __launch_bounds__(256, 5)
 grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
@@ -1427,11 +1631,30 @@ static int launch_search(const float *support, const float *query, int64_t B, in
     FFB6D_CUDA(cudaMemsetAsync(qs.state, 0, (size_t)B * sizeof(QueryState), st));
     const bool organised = K == 1 && !self && query_width >= 8 && Q % query_width == 0 && Q / query_width >= 4 &&
                            !g_force_thread_search;
+    bool far_sentinels = false;
     if (organised) {   // queries are an image: one warp per 8x4 pixel tile
-        const int64_t tiles = ceil_div(query_width, 8) * ceil_div(Q / query_width, 4);
+        const int64_t tiles_x = ceil_div(query_width, 8), tiles = tiles_x * ceil_div(Q / query_width, 4);
         dim3 tgrid((unsigned)ceil_div(tiles, 8), (unsigned)B);
-        grid_search_k1_tile_kernel<IdxT><<<tgrid, 256, 0, st>>>(
-            query, (int)S, (int)Q, (int)query_width, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+        if (env().k1_tile_old || tiles + tiles_x >= 4000000)   // the lean kernel's float reciprocals are exact below 2^22 tiles
+            grid_search_k1_tile_kernel<IdxT><<<tgrid, 256, 0, st>>>(
+                query, (int)S, (int)Q, (int)query_width, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+        else
+        {
+            far_sentinels = true;
+            const int qh = (int)(Q / query_width);
+            if (env().k1_tile_warps == 1)
+                grid_search_k1_tile2_kernel<IdxT, 1><<<dim3((unsigned)tiles, (unsigned)B), 32, 0, st>>>(
+                    query, (int)S, (int)Q, (int)query_width, qh, (int)tiles_x, (int)tiles, w.params, w.cursor, w.maxc,
+                    w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+            else if (env().k1_tile_warps == 2)
+                grid_search_k1_tile2_kernel<IdxT, 2><<<dim3((unsigned)ceil_div(tiles, 2), (unsigned)B), 64, 0, st>>>(
+                    query, (int)S, (int)Q, (int)query_width, qh, (int)tiles_x, (int)tiles, w.params, w.cursor, w.maxc,
+                    w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+            else
+                grid_search_k1_tile2_kernel<IdxT, 8><<<tgrid, 256, 0, st>>>(
+                    query, (int)S, (int)Q, (int)query_width, qh, (int)tiles_x, (int)tiles, w.params, w.cursor, w.maxc,
+                    w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
+        }
     } else if (warp && K <= 16) {   // half a warp per query
         dim3 ggrid((unsigned)ceil_div(Q, 16), (unsigned)B);
         if (self)
@@ -1464,6 +1687,11 @@ static int launch_search(const float *support, const float *query, int64_t B, in
         grid_overflow_warp_kernel<IdxT><<<ogrid, 256, 0, st>>>(support, query, (int)S, (int)Q, K, qs.state,
                                                                qs.ovf, (IdxT *)idx_out);
         FFB6D_LAUNCH_OK("grid_overflow_warp_kernel");
+        if (far_sentinels) {   // the lean tile kernel marked the duplicates of the far representative with -1
+            dim3 fgrid((unsigned)std::min<int64_t>(ceil_div(Q, 1024), 64), (unsigned)B);
+            grid_far_fill_kernel<IdxT><<<fgrid, 256, 0, st>>>((int)Q, qs.state, (IdxT *)idx_out);
+            FFB6D_LAUNCH_OK("grid_far_fill_kernel");
+        }
     } else {
         constexpr int OT = (KCAP >= 32) ? 64 : 128;
         dim3 ogrid((unsigned)std::min<int64_t>(ceil_div(Q, OT), per_item), (unsigned)B);

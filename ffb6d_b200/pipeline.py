@@ -24,7 +24,8 @@ class FusionPass:
     """
 
     def __init__(self, batch, n_points=12288, h=480, w=640, k=S.K_NEIGH, device="cuda",
-                 layout="nchw", seed=0, index_dtype=torch.int32, n_streams=2, n_gather_streams=None):
+                 layout="nchw", seed=0, index_dtype=torch.int32, n_streams=2, n_gather_streams=None,
+                 choose_first=None, interleave_builds=None):
         self.B, self.n_points, self.h, self.w, self.k = batch, n_points, h, w, k
         self.device = torch.device(device)
         self.layout = layout
@@ -41,6 +42,14 @@ class FusionPass:
         # grid builds: latency-bound cluster kernels, spread over streams of their own (FFB6D_BUILD_STREAMS, default 0 = share the search streams)
         nb = int(os.environ.get("FFB6D_BUILD_STREAMS", "0"))
         self.bstreams = [torch.cuda.Stream(device=self.device) for _ in range(nb)] if (n_streams > 1 and nb > 0) else []
+        # schedule switches (measured A/B, tools/pass_ab.py; results never depend on them):
+        # choose_first -- the `choose` gather depends on no search: it starts with the pass on a stream of its own and
+        #   streams its 2 GB of granule traffic underneath the latency-bound grid builds;
+        # interleave_builds -- every grid is built right before its first search instead of all grids first
+        self.choose_first = bool(int(os.environ.get("FFB6D_CHOOSE_FIRST", "0"))) if choose_first is None else bool(choose_first)
+        self.interleave_builds = (bool(int(os.environ.get("FFB6D_LAZY_BUILDS", "0"))) if interleave_builds is None
+                                  else bool(interleave_builds))
+        self.cstream = torch.cuda.Stream(device=self.device) if (n_streams > 1 and self.choose_first) else None
         self.gathers = S.gather_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.features = []
@@ -74,7 +83,7 @@ class FusionPass:
     def build_indices(self, cld, dpt_xyz, choose, timer=None, events=None):
         inputs = S.build_ffb6d_indices(cld, dpt_xyz, k=self.k, index_dtype=self.index_dtype,
                                        timer=timer, streams=self.streams, events=events, priority=self.priority,
-                                       build_streams=self.bstreams)
+                                       build_streams=self.bstreams, interleave_builds=self.interleave_builds)
         inputs["choose"] = choose
         return inputs
 
@@ -116,6 +125,19 @@ class FusionPass:
         gs = self.gstreams if events is not None else self.streams
         for st in gs:
             st.wait_stream(main)
+        extra = []
+        if self.cstream is not None and events is not None:
+            ci = [i for i in order if self.gathers[i][0] == "choose"]
+            order = [i for i in order if self.gathers[i][0] != "choose"]
+            self.cstream.wait_stream(main)
+            extra = [self.cstream]
+            for i in ci:                      # no index tensor to wait for
+                op, key, C, Sz, Q, K = self.gathers[i]
+                with torch.cuda.stream(self.cstream):
+                    outs[i] = self._gather(op, C, self.features[i], inputs[key])
+                if not capturing:
+                    inputs[key].record_stream(self.cstream)
+                    outs[i].record_stream(main)
         for j, i in enumerate(order):
             op, key, C, Sz, Q, K = self.gathers[i]
             st = gs[j % len(gs)]
@@ -128,7 +150,7 @@ class FusionPass:
                 # tell the caching allocator (inside a capture the graph's private pool keeps them alive)
                 inputs[key].record_stream(st)
                 outs[i].record_stream(main)
-        for st in (self.streams + self.gstreams + self.bstreams) if events is not None else gs:
+        for st in (self.streams + self.gstreams + self.bstreams + extra) if events is not None else gs:
             main.wait_stream(st)
         if events is not None:
             events.pop("_keepalive", None)   # every search has been joined: the grids may go
@@ -186,7 +208,7 @@ class FusionPass:
         events = {} if self.streams is not None else None
         inputs = S.build_ffb6d_indices(cld, None, k=self.k, index_dtype=self.index_dtype, streams=self.streams,
                                        pyramid=pyr, image_hw=(self.h, self.w), events=events, priority=self.priority,
-                                       build_streams=self.bstreams)
+                                       build_streams=self.bstreams, interleave_builds=self.interleave_builds)
         inputs["choose"] = choose
         return inputs, self.run_gathers(inputs, events=events)
 
