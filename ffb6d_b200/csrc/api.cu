@@ -63,11 +63,7 @@ const Env &env()
         v.mlp_no_pair_tiles = on("FFB6D_MLP_NO_MT2");
         v.check_indices = on("FFB6D_CHECK_INDICES");
         v.grid_thread_search = on("FFB6D_GRID_THREAD_SEARCH");
-        v.k1_tile_old = on("FFB6D_K1_TILE_OLD");
-        v.k1_tile_warps = getenv("FFB6D_K1_TILE_WARPS") ? atoi(getenv("FFB6D_K1_TILE_WARPS")) : 8;
-        v.gather_noalloc = on("FFB6D_GATHER_NOALLOC");
-        v.gather_smem_pad = getenv("FFB6D_GATHER_SMEM_PAD") ? atoi(getenv("FFB6D_GATHER_SMEM_PAD")) : 0;
-        if (v.gather_smem_pad < 0 || v.gather_smem_pad > 47 * 1024) v.gather_smem_pad = 0;
+        v.subset_nn = on("FFB6D_SUBSET_NN");
         const char *x;
         v.grid_scale = (x = getenv("FFB6D_GRID_SCALE")) ? (float)atof(x) : 1.0f;
         v.grid_scale_k1 = (x = getenv("FFB6D_GRID_SCALE_K1")) ? (float)atof(x) : 2.5f;
@@ -236,6 +232,21 @@ int ffb6d_knn_grid_query_organized(const float *support, const float *query, int
     FFB6D_CHECK_ARG(support && query && idx_out && grid && scratch, "knn_grid_query: null pointer");
     return knn_grid_query(support, query, B, S, Q, K, idx_out, idx_is_i64, grid, grid_bytes, scratch,
                           scratch_bytes, (cudaStream_t)stream, query_width);
+}
+
+int ffb6d_knn_subset_nn(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, const void *knn_idx,
+                        int K_list, void *idx_out, int idx_is_i64, void *scratch, size_t scratch_bytes,
+                        ffb6d_stream_t stream)
+{
+    FFB6D_CHECK_ARG(B >= 0 && S >= 1 && Q >= 0 && B < 65536 && S < (1ll << 31) && Q < (1ll << 31),
+                    "knn_subset_nn: bad size");
+    FFB6D_CHECK_ARG(S <= Q || Q == 0, "knn_subset_nn: the support (%lld rows) must be a row prefix of the %lld queries",
+                    (long long)S, (long long)Q);
+    FFB6D_CHECK_ARG(K_list >= 1 && K_list <= FFB6D_MAX_K, "knn_subset_nn: K_list=%d outside [1,%d]", K_list, FFB6D_MAX_K);
+    if (B == 0 || Q == 0) return FFB6D_OK;
+    FFB6D_CHECK_ARG(support && query && knn_idx && idx_out && scratch, "knn_subset_nn: null pointer");
+    return knn_subset_nn_from_knn(support, query, B, S, Q, knn_idx, K_list, idx_out, idx_is_i64, scratch, scratch_bytes,
+                                  (cudaStream_t)stream);
 }
 
 void ffb6d_knn_grid_tune(float cell_scale, int quantile) { knn_grid_tune(cell_scale, quantile); }

@@ -82,10 +82,7 @@ struct Env {
     bool mlp_no_pair_tiles; // FFB6D_MLP_NO_MT2=1: one 128-row weight tile per CTA for every layer (A/B timing)
     bool check_indices;     // FFB6D_CHECK_INDICES=1: validate gather indices (synchronises; debugging aid)
     bool grid_thread_search;
-    bool k1_tile_old;       // FFB6D_K1_TILE_OLD=1: the first organised K = 1 tile kernel (A/B timing)
-    int k1_tile_warps;      // FFB6D_K1_TILE_WARPS=8|2|1: warps (tiles) per CTA of the lean tile kernel
-    bool gather_noalloc;    // FFB6D_GATHER_NOALLOC=1: sparse gathers read their rows with ld.global.nc.L1::no_allocate
-    int gather_smem_pad;    // FFB6D_GATHER_SMEM_PAD=bytes (< 48 K) of unused dynamic shared memory for the K-lane / direct gathers (caps their CTAs per SM)
+    bool subset_nn;         // FFB6D_SUBSET_NN=1: ffb6d_build_indices reads cld_interp_idx{0,1} off the self searches (ffb6d_knn_subset_nn)
     float grid_scale, grid_scale_k1;
     int grid_quantile;
 };

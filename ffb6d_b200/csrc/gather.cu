@@ -33,15 +33,6 @@ __device__ __forceinline__ float max_nan(float m, float v)
     return r;
 }
 
-// read-only load that does not allocate in L1 (rows of the sparse gathers are touched once per CTA: keeping them
-// out of L1 leaves it to the search kernels that share the SM)
-__device__ __forceinline__ float ldg_na(const float *p)
-{
-    float v;
-    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(v) : "l"(p));
-    return v;
-}
-
 template <typename IdxT, int KT>
 __device__ __forceinline__ void load_ids(const IdxT *__restrict__ ip, int K, int (&id)[KT > 0 ? KT : 1])
 {
@@ -272,7 +263,7 @@ gather_max_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restr
 template <typename IdxT, int KT>
 __global__ void __launch_bounds__(256)
 gather_max_ncs_klane_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
-                            float *__restrict__ out, int C, int S, int Q, int na)
+                            float *__restrict__ out, int C, int S, int Q)
 {
     constexpr int TQ = 32;            // queries per CTA tile (one 128-byte output segment per channel)
     constexpr int QPW = 32 / KT;      // queries per warp at a time
@@ -295,8 +286,7 @@ gather_max_ncs_klane_kernel(const float *__restrict__ feat, const IdxT *__restri
             for (int c = 0; c < cc; c += 4) {   // four independent loads in flight
                 float v[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u)
-                    v[u] = (c + u < cc) ? (na ? ldg_na(src + (size_t)(c + u) * S) : __ldg(src + (size_t)(c + u) * S)) : 0.f;
+                for (int u = 0; u < 4; ++u) v[u] = (c + u < cc) ? __ldg(src + (size_t)(c + u) * S) : 0.f;
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
 #pragma unroll
@@ -318,7 +308,7 @@ gather_max_ncs_klane_kernel(const float *__restrict__ feat, const IdxT *__restri
 template <typename IdxT>
 __global__ void __launch_bounds__(256)
 gather1_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restrict__ idx,
-                          float *__restrict__ out, int C, int S, int Q, int na)
+                          float *__restrict__ out, int C, int S, int Q)
 {
     const int b = blockIdx.z;
     const int c0 = blockIdx.y * 8;
@@ -329,7 +319,7 @@ gather1_ncs_direct_kernel(const float *__restrict__ feat, const IdxT *__restrict
     float *dst = out + ((size_t)b * C + c0) * Q + q;
     float v[8];
 #pragma unroll
-    for (int c = 0; c < 8; ++c) v[c] = (c0 + c < C) ? (na ? ldg_na(src + (size_t)c * S) : __ldg(src + (size_t)c * S)) : 0.f;
+    for (int c = 0; c < 8; ++c) v[c] = (c0 + c < C) ? __ldg(src + (size_t)c * S) : 0.f;
 #pragma unroll
     for (int c = 0; c < 8; ++c)
         if (c0 + c < C) __stcs(dst + (size_t)c * Q, v[c]);
@@ -714,14 +704,12 @@ static int launch_ncs(const float *feat, const IdxT *idx, float *out, int64_t B,
         FFB6D_LAUNCH_OK("gather_max_ncs_staged_kernel");
     } else if (KT == 1) {
         dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)ceil_div(C, 8), (unsigned)B);
-        gather1_ncs_direct_kernel<IdxT><<<grid, 256, env().gather_smem_pad, st>>>(feat, idx, out, (int)C, (int)S, (int)Q,
-                                                                                 (int)env().gather_noalloc);
+        gather1_ncs_direct_kernel<IdxT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
         FFB6D_LAUNCH_OK("gather1_ncs_direct_kernel");
     } else if ((KT == 8 || KT == 16 || KT == 32) && !env().gather_direct) {
         if constexpr (KT == 8 || KT == 16 || KT == 32) {
             dim3 grid((unsigned)ceil_div(Q, 32), (unsigned)std::min<int64_t>(ceil_div(C, 8), 65535), (unsigned)B);
-            gather_max_ncs_klane_kernel<IdxT, KT><<<grid, 256, env().gather_smem_pad, st>>>(feat, idx, out, (int)C, (int)S, (int)Q,
-                                                                                           (int)env().gather_noalloc);
+            gather_max_ncs_klane_kernel<IdxT, KT><<<grid, 256, 0, st>>>(feat, idx, out, (int)C, (int)S, (int)Q);
             FFB6D_LAUNCH_OK("gather_max_ncs_klane_kernel");
         }
     } else {

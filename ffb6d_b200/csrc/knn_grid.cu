@@ -652,166 +652,6 @@ grid_search_kernel(const float *__restrict__ query, int S, int Q, int K,
     register_overflow(query, Q, b, q, qx, qy, qz, state_all, ovf_all);
 }
 
-// ------------------------------------------------------------------ E0. K = 1, ORGANISED queries: one warp per 8x4 pixel tile
-// The p2r searches of the schedule ask for the nearest cloud point of every pixel of an image pyramid
-// level (ycb_dataset.py:291-293, 305-308): 94 % of all K = 1 queries.  Neighbouring pixels are
-// neighbouring points, so the 32 queries of an 8 x 4 pixel tile share ONE candidate set: the cells of
-// the bounding box of their own cells, grown by one cell.  All lanes walk the same candidate list
-// (warp-uniform addresses: one L1 broadcast per candidate, no divergence -- the thread-per-query kernel
-// runs at 14.5 of 32 lanes active) and certify their own result against the distance to the box faces.
-// The few lanes that cannot be certified (near depth discontinuities, box too large) are compacted per
-// CTA and finished by the per-thread ring search; hole pixels (far outside the support) go straight to
-// the overflow list as before.
-template <typename IdxT>
-__global__ void __launch_bounds__(256, 4)
-grid_search_k1_tile_kernel(const float *__restrict__ query, int S, int Q, int qw,
-                           const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
-                           size_t cursor_stride, const float4 *__restrict__ sorted_all,
-                           IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
-{
-    constexpr int TW = 8, TH = 4;               // tile = 8 x 4 pixels
-    constexpr int MAX_ROWS = 32, MAX_X = 8;     // widest shared box: 32 cell rows of up to 8 cells
-    constexpr int TILE_CAND = 128;              // candidates staged per round and warp
-    __shared__ float4 s_cand[8][TILE_CAND];
-    __shared__ int s_list[256];
-    __shared__ int s_count;
-    const unsigned FULL = 0xffffffffu;
-    const int b = blockIdx.y;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    const int qh = Q / qw;
-    const int tiles_x = (qw + TW - 1) / TW, tiles_y = (qh + TH - 1) / TH;
-    const int tile = blockIdx.x * 8 + wid;
-    const GridParams Ps = params_all[b];
-    const int *cell_end = cursor_all + (size_t)b * cursor_stride;
-    const float4 *sorted = sorted_all + (size_t)b * S;
-    const float INF = __int_as_float(0x7f800000);
-    if (threadIdx.x == 0) s_count = 0;
-    __syncthreads();
-
-    const int px = (tile % tiles_x) * TW + (lane & (TW - 1)), py = (tile / tiles_x) * TH + lane / TW;
-    const bool inimg = tile < tiles_x * tiles_y && px < qw && py < qh;
-    const int q = inimg ? py * qw + px : 0;
-    float qx = 0.f, qy = 0.f, qz = 0.f;
-    if (inimg) {
-        const float *qp = query + ((size_t)b * Q + q) * 3;
-        qx = __ldg(qp);
-        qy = __ldg(qp + 1);
-        qz = __ldg(qp + 2);
-    }
-    const int nx = Ps.n[0], ny = Ps.n[1], nz = Ps.n[2];
-    const float h = Ps.h, slack = Ps.slack;
-    const float out = fmaxf(fmaxf(fmaxf(Ps.lo[0] - qx, qx - Ps.hi[0]), fmaxf(Ps.lo[1] - qy, qy - Ps.hi[1])),
-                            fmaxf(Ps.lo[2] - qz, qz - Ps.hi[2]));
-    // state: 0 answered, 1 finish with the ring search, 2 overflow (far from the support), 3 no query
-    int state = !inimg ? 3 : ((out > (float)RMAX * h || !(qx == qx && qy == qy && qz == qz)) ? 2 : 1);
-    const bool part = state == 1;
-    const int cx = cell_of(qx, Ps.lo[0], Ps.inv_h, nx);
-    const int cy = cell_of(qy, Ps.lo[1], Ps.inv_h, ny);
-    const int cz = cell_of(qz, Ps.lo[2], Ps.inv_h, nz);
-    const int big = 0x3fffffff;
-    int X0 = __reduce_min_sync(FULL, part ? cx : big), X1 = __reduce_max_sync(FULL, part ? cx : -1);
-    int Y0 = __reduce_min_sync(FULL, part ? cy : big), Y1 = __reduce_max_sync(FULL, part ? cy : -1);
-    int Z0 = __reduce_min_sync(FULL, part ? cz : big), Z1 = __reduce_max_sync(FULL, part ? cz : -1);
-    if (X1 >= 0) {   // warp-uniform: somebody takes part
-        X0 = max(X0 - 1, 0); X1 = min(X1 + 1, nx - 1);
-        Y0 = max(Y0 - 1, 0); Y1 = min(Y1 + 1, ny - 1);
-        Z0 = max(Z0 - 1, 0); Z1 = min(Z1 + 1, nz - 1);
-        const int by = Y1 - Y0 + 1, nrows = by * (Z1 - Z0 + 1);
-        if (nrows <= MAX_ROWS && X1 - X0 + 1 <= MAX_X) {
-            int beg = 0, end = 0;
-            if (lane < nrows) {   // lane r looks up cell row r of the box
-                const int row = ((Z0 + lane / by) * ny + (Y0 + lane % by)) * nx;
-                beg = (row + X0 > 0) ? __ldg(cell_end + row + X0 - 1) : 0;
-                end = __ldg(cell_end + row + X1);
-            }
-            // the rows' point ranges are flattened (warp prefix sum) and the candidates staged in shared
-            // memory 128 at a time by all lanes in parallel; then every lane walks the same staged list
-            // (broadcast LDS.128): no per-row loop overhead, no divergence
-            const int cnt = end - beg;
-            int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int u = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += u;
-            }
-            const int total = __shfl_sync(FULL, incl, 31);
-            const int excl = incl - cnt;
-            float4 *stage = s_cand[wid];
-            float bd = INF;
-            int bi = 0;
-            for (int c0 = 0; c0 < total; c0 += TILE_CAND) {
-                const int n = min(TILE_CAND, total - c0);
-                __syncwarp();
-#pragma unroll
-                for (int u = 0; u < TILE_CAND / 32; ++u) {
-                    const int j = c0 + u * 32 + lane;
-                    int seg = 0;   // number of rows whose inclusive count is <= j
-#pragma unroll
-                    for (int step = 16; step > 0; step >>= 1) {
-                        const int v = __shfl_sync(FULL, incl, seg + step - 1);
-                        if (v <= j) seg += step;
-                    }
-                    const int sb = __shfl_sync(FULL, beg, seg & 31), se = __shfl_sync(FULL, excl, seg & 31);
-                    if (j < total) stage[u * 32 + lane] = __ldg(sorted + sb + (j - se));
-                }
-                __syncwarp();
-                for (int p = 0; p < n; p += 4) {
-                    float4 c[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) c[u] = stage[min(p + u, n - 1)];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) {
-                        const float d = ref_sqdist(qx, qy, qz, c[u].x, c[u].y, c[u].z);
-                        const int id = __float_as_int(c[u].w);
-                        if (p + u < n && (d < bd || (d == bd && id < bi))) {
-                            bd = d;
-                            bi = id;
-                        }
-                    }
-                }
-            }
-            if (part) {
-                // distance to the nearest face of the box that still has cells behind it
-                float m = INF;
-                if (X0 > 0) m = fminf(m, qx - (Ps.lo[0] + (float)X0 * h));
-                if (X1 < nx - 1) m = fminf(m, (Ps.lo[0] + (float)(X1 + 1) * h) - qx);
-                if (Y0 > 0) m = fminf(m, qy - (Ps.lo[1] + (float)Y0 * h));
-                if (Y1 < ny - 1) m = fminf(m, (Ps.lo[1] + (float)(Y1 + 1) * h) - qy);
-                if (Z0 > 0) m = fminf(m, qz - (Ps.lo[2] + (float)Z0 * h));
-                if (Z1 < nz - 1) m = fminf(m, (Ps.lo[2] + (float)(Z1 + 1) * h) - qz);
-                const float ms = m - slack;
-                const bool ok = (m == INF) ? (bd < INF || S == 0) : (ms > 0.f && bd <= ms * ms * (1.0f - 1e-5f));
-                if (ok) {
-                    idx_out[(size_t)b * Q + q] = (IdxT)bi;
-                    state = 0;
-                }
-            }
-        }
-    }
-    // ---- the uncertified queries of the CTA, compacted, finished by the per-thread ring search
-    if (state == 1) s_list[atomicAdd(&s_count, 1)] = q;
-    __syncthreads();
-    const int n_retry = s_count;
-    int q2 = -1;
-    float rx = 0.f, ry = 0.f, rz = 0.f;
-    bool retry_failed = false;
-    if ((int)threadIdx.x < n_retry) {
-        q2 = s_list[threadIdx.x];
-        const float *qp = query + ((size_t)b * Q + q2) * 3;
-        rx = __ldg(qp);
-        ry = __ldg(qp + 1);
-        rz = __ldg(qp + 2);
-        TopK<1> top;
-        top.init();
-        if (thread_search<1>(rx, ry, rz, 1, Ps, cell_end, sorted, top))
-            idx_out[(size_t)b * Q + q2] = (IdxT)top.i[0];
-        else
-            retry_failed = true;
-    }
-    if (retry_failed) register_overflow(query, Q, b, q2, rx, ry, rz, state_all, ovf_all);
-    if (state == 2) register_overflow(query, Q, b, q, qx, qy, qz, state_all, ovf_all);
-}
-
 // ------------------------------------------------------------------ E'. search, one WARP per query
 // For 2 <= K <= 32.  The sorted top list lives across the lanes (lane j holds the j-th best) as
 // one 64-bit key per entry, (distance bits << 32) | index: squared distances are non-negative so
@@ -887,6 +727,16 @@ __device__ __forceinline__ void warp_list_offer(key_t64 &mine, key_t64 cand, int
     }
 }
 
+// ------------------------------------------------------------------ E0. K = 1, ORGANISED queries: one warp per 8x4 pixel tile
+// The p2r searches of the schedule ask for the nearest cloud point of every pixel of an image pyramid
+// level (ycb_dataset.py:291-293, 305-308): 94 % of all K = 1 queries.  Neighbouring pixels are
+// neighbouring points, so the 32 queries of an 8 x 4 pixel tile share ONE candidate set: the cells of
+// the bounding box of their own cells, grown by one cell.  All lanes walk the same candidate list
+// (warp-uniform addresses: one shared-memory broadcast per candidate, no divergence -- the thread-per-query
+// kernel runs at 14.5 of 32 lanes active) and certify their own result against the distance to the box faces.
+// The few lanes that cannot be certified (near depth discontinuities, box too large) are finished by the
+// per-thread ring search; hole pixels (far outside the support) are marked and filled afterwards (below).
+
 // Far queries of an ORGANISED K = 1 search (the hole pixels of an image level: ~10 % of the queries, all at the
 // origin).  register_overflow() costs every tile a same-address atomicAdd on the item's dup counter -- 2400 warps
 // per frame queue on one L2 atomic unit, half of the tile kernel's stall samples (ncu source page) -- and leaves the
@@ -933,20 +783,21 @@ grid_far_fill_kernel(int Q, const QueryState *__restrict__ state_all, IdxT *__re
         if (o[q] == (IdxT)-1) o[q] = v;
 }
 
-// ------------------------------------------------------------------ E0'. the same tile search, lean issue path
-// grid_search_k1_tile_kernel spends two thirds of its ~1300 warp instructions per tile outside the distance
-// arithmetic (SASS: 93 instructions per 4 candidates in the walk, a third of them uniform-datapath bound checks;
-// 190 for a staging round that always runs four binary-search sub-batches; integer divisions in the prologue).
-// This version keeps the algorithm and the certificate and removes that overhead:
+// The tile kernel.  Issue path kept lean (the first version spent two thirds of its ~1300 warp instructions per tile
+// outside the distance arithmetic: 93 SASS instructions per 4 candidates in the walk, a third of them uniform-datapath
+// bound checks; 190 for a staging round that always ran four binary-search sub-batches; integer divisions):
 //   * the staged list is padded to a multiple of four with sentinel candidates at +inf (their key sorts after
-//     every real candidate), so the walk has no per-candidate bound checks and its LDS.128 use immediate offsets;
+//     every real candidate), so the walk has no per-candidate bound checks and its LDS.128 use immediate offsets
+//     (109 instructions per 8 candidates);
 //   * best-so-far is ONE 64-bit key (distance bits << 32 | index): the total order is a single unsigned compare;
 //   * staging runs only as many 32-candidate sub-batches as there are candidates;
-//   * tile and row coordinates come from exact float reciprocals instead of integer divisions (host passes the
-//     tile counts; (i + 0.5) * (1 / n) truncates to i / n whenever i < 2^22, guaranteed by the launcher).
+//   * tile and row coordinates come from exact float reciprocals instead of integer divisions when the tile count
+//     allows it ((i + 0.5) * (1 / n) truncates to i / n whenever i + n < 2^22; `exact_div` selects the division).
+// NW = warps (tiles) per CTA; one-warp CTAs need no CTA barrier around the retry list (measured 2.805 / 2.813 /
+// 2.831 ms per pass for NW = 1 / 2 / 8).
 template <typename IdxT, int NW>
 __global__ void __launch_bounds__(NW * 32, 1024 / (NW * 32))
-grid_search_k1_tile2_kernel(const float *__restrict__ query, int S, int Q, int qw, int qh, int tiles_x, int n_tiles,
+grid_search_k1_tile_kernel(const float *__restrict__ query, int S, int Q, int qw, int qh, int tiles_x, int n_tiles, int exact_div,
                             const GridParams *__restrict__ params_all, const int *__restrict__ cursor_all,
                             size_t cursor_stride, const float4 *__restrict__ sorted_all,
                             IdxT *__restrict__ idx_out, QueryState *state_all, int *__restrict__ ovf_all)
@@ -969,7 +820,7 @@ grid_search_k1_tile2_kernel(const float *__restrict__ query, int S, int Q, int q
     if (NW > 1) __syncthreads();
     else __syncwarp();
 
-    const int trow = (int)(((float)tile + 0.5f) * (1.0f / (float)tiles_x));   // == tile / tiles_x (see above)
+    const int trow = exact_div ? tile / tiles_x : (int)(((float)tile + 0.5f) * (1.0f / (float)tiles_x));   // == tile / tiles_x
     const int px = (tile - trow * tiles_x) * TW + (lane & (TW - 1)), py = trow * TH + (lane >> 3);
     const bool inimg = tile < n_tiles && px < qw && py < qh;
     const int q = inimg ? py * qw + px : 0;
@@ -1091,6 +942,7 @@ grid_search_k1_tile2_kernel(const float *__restrict__ query, int S, int Q, int q
     if (state == 2) register_far_k1<IdxT>(query, Q, b, q, qx, qy, qz, state_all, ovf_all, idx_out);
 }
 
+// ------------------------------------------------------------------ E'. (continued) the warp-per-query kernel
 template <typename IdxT, bool SELF>
 __global__ void __launch_bounds__(256, 5)
 grid_search_warp_kernel(const float *__restrict__ query, int S, int Q, int K,
@@ -1588,6 +1440,68 @@ grid_dup_copy_kernel(int Q, int K, const QueryState *__restrict__ state_all,
     }
 }
 
+// ------------------------------------------------------------------ H. nearest point of a row-PREFIX subset, read off a self search
+// The schedule asks, per cloud level i, for the nearest level-(i+1) point of every level-i point (cld_interp_idx{i},
+// ycb_dataset.py:280-282).  Level i+1 is the first N_{i+1} rows of level i (:278) and the K-neighbour self search of
+// level i (cld_nei_idx{i}) has just been computed: its rows are sorted by the total order (distance, index) over ALL
+// level-i points, so the first entry of a row with index < N_{i+1} IS the nearest subset point under the same total
+// order -- every subset point that is not in the row sorts after the row's last entry.  Only rows without such an
+// entry (0.75^16 = 1 % of the queries when the subset is a random quarter) need a search: they go to the full-scan
+// pass (one CTA per query).  No grid is needed.
+template <typename IdxT>
+__global__ void __launch_bounds__(256)
+subset_nn_from_knn_kernel(const IdxT *__restrict__ knn, int Q, int KL, int S, IdxT *__restrict__ idx_out,
+                          QueryState *state_all, int *__restrict__ ovf_all)
+{
+    const int b = blockIdx.y;
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= Q) return;
+    const IdxT *row = knn + ((size_t)b * Q + q) * KL;
+    const int kl = min(KL, Q);   // a level smaller than KL leaves (+inf, 0) fillers behind its Q real entries
+    for (int j = 0; j < kl; ++j) {
+        const IdxT v = __ldg(row + j);
+        if (v >= 0 && v < (IdxT)S) {
+            idx_out[(size_t)b * Q + q] = v;
+            return;
+        }
+    }
+    auto g = cooperative_groups::coalesced_threads();
+    int base = 0;
+    if (g.thread_rank() == 0) base = atomicAdd(&state_all[b].ovf_count, (int)g.size());
+    ovf_all[(size_t)b * Q + g.shfl(base, 0) + (int)g.thread_rank()] = q;
+}
+
+// support = the first S rows of `query` in every batch item ([B,S,3] contiguous copy), knn = the exact K-neighbour
+// self search of `query` ([B,Q,KL], rows sorted by (distance, index)); idx_out [B,Q,1]
+int knn_subset_nn_from_knn(const float *support, const float *query, int64_t B, int64_t S, int64_t Q, const void *knn,
+                           int KL, void *idx_out, int idx_is_i64, void *scratch, size_t scratch_bytes, cudaStream_t st)
+{
+    QueryScratch qs = carve_query(scratch, B, Q);
+    if (!scratch || scratch_bytes < qs.bytes) {
+        set_error("knn subset search: %zu bytes of scratch required, %zu given", qs.bytes, scratch_bytes);
+        return FFB6D_ERR_WORKSPACE;
+    }
+    FFB6D_CUDA(cudaMemsetAsync(qs.state, 0, (size_t)B * sizeof(QueryState), st));
+    dim3 grid((unsigned)ceil_div(Q, 256), (unsigned)B);
+    const int64_t per_item = std::max<int64_t>(1, 4 * num_sms() / B);
+    dim3 ogrid((unsigned)std::min<int64_t>(Q, per_item), (unsigned)B);
+    if (idx_is_i64) {
+        subset_nn_from_knn_kernel<long long><<<grid, 256, 0, st>>>((const long long *)knn, (int)Q, KL, (int)S,
+                                                                   (long long *)idx_out, qs.state, qs.ovf);
+        FFB6D_LAUNCH_OK("subset_nn_from_knn_kernel");
+        grid_overflow_warp_kernel<long long><<<ogrid, 256, 0, st>>>(support, query, (int)S, (int)Q, 1, qs.state, qs.ovf,
+                                                                    (long long *)idx_out);
+    } else {
+        subset_nn_from_knn_kernel<int><<<grid, 256, 0, st>>>((const int *)knn, (int)Q, KL, (int)S, (int *)idx_out, qs.state,
+                                                             qs.ovf);
+        FFB6D_LAUNCH_OK("subset_nn_from_knn_kernel");
+        grid_overflow_warp_kernel<int><<<ogrid, 256, 0, st>>>(support, query, (int)S, (int)Q, 1, qs.state, qs.ovf,
+                                                              (int *)idx_out);
+    }
+    FFB6D_LAUNCH_OK("grid_overflow_warp_kernel");
+    return FFB6D_OK;
+}
+
 // ------------------------------------------------------------------ host
 // cell-size knobs: defaults from the environment (read once, common.cuh Env), overridable by
 // ffb6d_knn_grid_tune* (tools/tune_grid.py); results never depend on them
@@ -1634,27 +1548,10 @@ static int launch_search(const float *support, const float *query, int64_t B, in
     bool far_sentinels = false;
     if (organised) {   // queries are an image: one warp per 8x4 pixel tile
         const int64_t tiles_x = ceil_div(query_width, 8), tiles = tiles_x * ceil_div(Q / query_width, 4);
-        dim3 tgrid((unsigned)ceil_div(tiles, 8), (unsigned)B);
-        if (env().k1_tile_old || tiles + tiles_x >= 4000000)   // the lean kernel's float reciprocals are exact below 2^22 tiles
-            grid_search_k1_tile_kernel<IdxT><<<tgrid, 256, 0, st>>>(
-                query, (int)S, (int)Q, (int)query_width, w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
-        else
-        {
-            far_sentinels = true;
-            const int qh = (int)(Q / query_width);
-            if (env().k1_tile_warps == 1)
-                grid_search_k1_tile2_kernel<IdxT, 1><<<dim3((unsigned)tiles, (unsigned)B), 32, 0, st>>>(
-                    query, (int)S, (int)Q, (int)query_width, qh, (int)tiles_x, (int)tiles, w.params, w.cursor, w.maxc,
-                    w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
-            else if (env().k1_tile_warps == 2)
-                grid_search_k1_tile2_kernel<IdxT, 2><<<dim3((unsigned)ceil_div(tiles, 2), (unsigned)B), 64, 0, st>>>(
-                    query, (int)S, (int)Q, (int)query_width, qh, (int)tiles_x, (int)tiles, w.params, w.cursor, w.maxc,
-                    w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
-            else
-                grid_search_k1_tile2_kernel<IdxT, 8><<<tgrid, 256, 0, st>>>(
-                    query, (int)S, (int)Q, (int)query_width, qh, (int)tiles_x, (int)tiles, w.params, w.cursor, w.maxc,
-                    w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
-        }
+        far_sentinels = true;
+        grid_search_k1_tile_kernel<IdxT, 1><<<dim3((unsigned)tiles, (unsigned)B), 32, 0, st>>>(
+            query, (int)S, (int)Q, (int)query_width, (int)(Q / query_width), (int)tiles_x, (int)tiles,
+            (int)(tiles + tiles_x >= 4000000), w.params, w.cursor, w.maxc, w.sorted, (IdxT *)idx_out, qs.state, qs.ovf);
     } else if (warp && K <= 16) {   // half a warp per query
         dim3 ggrid((unsigned)ceil_div(Q, 16), (unsigned)B);
         if (self)

@@ -24,8 +24,7 @@ class FusionPass:
     """
 
     def __init__(self, batch, n_points=12288, h=480, w=640, k=S.K_NEIGH, device="cuda",
-                 layout="nchw", seed=0, index_dtype=torch.int32, n_streams=2, n_gather_streams=None,
-                 choose_first=None, interleave_builds=None):
+                 layout="nchw", seed=0, index_dtype=torch.int32, n_streams=2, n_gather_streams=None):
         self.B, self.n_points, self.h, self.w, self.k = batch, n_points, h, w, k
         self.device = torch.device(device)
         self.layout = layout
@@ -41,15 +40,9 @@ class FusionPass:
                           for _ in range(n_gather_streams or n_streams)] if n_streams > 1 else None)
         # grid builds: latency-bound cluster kernels, spread over streams of their own (FFB6D_BUILD_STREAMS, default 0 = share the search streams)
         nb = int(os.environ.get("FFB6D_BUILD_STREAMS", "0"))
-        self.bstreams = [torch.cuda.Stream(device=self.device) for _ in range(nb)] if (n_streams > 1 and nb > 0) else []
-        # schedule switches (measured A/B, tools/pass_ab.py; results never depend on them):
-        # choose_first -- the `choose` gather depends on no search: it starts with the pass on a stream of its own and
-        #   streams its 2 GB of granule traffic underneath the latency-bound grid builds;
-        # interleave_builds -- every grid is built right before its first search instead of all grids first
-        self.choose_first = bool(int(os.environ.get("FFB6D_CHOOSE_FIRST", "0"))) if choose_first is None else bool(choose_first)
-        self.interleave_builds = (bool(int(os.environ.get("FFB6D_LAZY_BUILDS", "0"))) if interleave_builds is None
-                                  else bool(interleave_builds))
-        self.cstream = torch.cuda.Stream(device=self.device) if (n_streams > 1 and self.choose_first) else None
+        bp = int(os.environ.get("FFB6D_BUILD_PRIO", "0"))
+        self.bstreams = ([torch.cuda.Stream(device=self.device, priority=bp) for _ in range(nb)]
+                         if (n_streams > 1 and nb > 0) else [])
         self.gathers = S.gather_schedule(n_points, h, w)
         g = torch.Generator(device=self.device).manual_seed(seed)
         self.features = []
@@ -66,6 +59,8 @@ class FusionPass:
         unlocked = {}
         derived = S.derived_searches(S.knn_schedule(n_points, h, w, k))   # row slices of another search
         derived.update({c: p_ for c, (p_, f_) in S.derived_image_searches(S.knn_schedule(n_points, h, w, k), h, w).items()})
+        if k >= 8 and os.environ.get("FFB6D_SUBSET_NN", "0") == "1":   # cld_interp_idx{i} is read off cld_nei_idx{i} (schedule.py)
+            derived.update(S.derived_subset_searches(S.knn_schedule(n_points, h, w, k)))
         for op, key, C, Sz, Q, K in self.gathers:
             src = key.replace("cld_sub_idx", "cld_nei_idx")
             src = derived.get(src, src)
@@ -74,6 +69,10 @@ class FusionPass:
         if os.environ.get("FFB6D_SCHED", "unlock") == "unlock":   # "size": largest search first (3.63 vs 3.59 ms)
             self.priority = {key: unlocked.get(key, 0) / float(S.set_size(q, n_points, h, w) * (12 if kk > 1 else 1))
                              for key, s_, q, kk in S.knn_schedule(n_points, h, w, k)}
+        # ... except the level-0 self search, the longest search of the pass: it needs only the level-0 grid, so it goes
+        # first and the big p2r searches queue behind it (measured three times: -0.2 ... -0.6 % of the pass)
+        if self.priority is not None and os.environ.get("FFB6D_SELF_FIRST", "1") != "0":
+            self.priority["cld_nei_idx0"] = float("inf")
         kb, gb = S.frame_alg_bytes(n_points, h, w, k)
         self.alg_bytes_per_frame = kb + gb
         self.knn_alg_bytes_per_frame = kb
@@ -83,7 +82,7 @@ class FusionPass:
     def build_indices(self, cld, dpt_xyz, choose, timer=None, events=None):
         inputs = S.build_ffb6d_indices(cld, dpt_xyz, k=self.k, index_dtype=self.index_dtype,
                                        timer=timer, streams=self.streams, events=events, priority=self.priority,
-                                       build_streams=self.bstreams, interleave_builds=self.interleave_builds)
+                                       build_streams=self.bstreams)
         inputs["choose"] = choose
         return inputs
 
@@ -125,19 +124,6 @@ class FusionPass:
         gs = self.gstreams if events is not None else self.streams
         for st in gs:
             st.wait_stream(main)
-        extra = []
-        if self.cstream is not None and events is not None:
-            ci = [i for i in order if self.gathers[i][0] == "choose"]
-            order = [i for i in order if self.gathers[i][0] != "choose"]
-            self.cstream.wait_stream(main)
-            extra = [self.cstream]
-            for i in ci:                      # no index tensor to wait for
-                op, key, C, Sz, Q, K = self.gathers[i]
-                with torch.cuda.stream(self.cstream):
-                    outs[i] = self._gather(op, C, self.features[i], inputs[key])
-                if not capturing:
-                    inputs[key].record_stream(self.cstream)
-                    outs[i].record_stream(main)
         for j, i in enumerate(order):
             op, key, C, Sz, Q, K = self.gathers[i]
             st = gs[j % len(gs)]
@@ -150,7 +136,7 @@ class FusionPass:
                 # tell the caching allocator (inside a capture the graph's private pool keeps them alive)
                 inputs[key].record_stream(st)
                 outs[i].record_stream(main)
-        for st in (self.streams + self.gstreams + self.bstreams + extra) if events is not None else gs:
+        for st in (self.streams + self.gstreams + self.bstreams) if events is not None else gs:
             main.wait_stream(st)
         if events is not None:
             events.pop("_keepalive", None)   # every search has been joined: the grids may go
@@ -208,7 +194,7 @@ class FusionPass:
         events = {} if self.streams is not None else None
         inputs = S.build_ffb6d_indices(cld, None, k=self.k, index_dtype=self.index_dtype, streams=self.streams,
                                        pyramid=pyr, image_hw=(self.h, self.w), events=events, priority=self.priority,
-                                       build_streams=self.bstreams, interleave_builds=self.interleave_builds)
+                                       build_streams=self.bstreams)
         inputs["choose"] = choose
         return inputs, self.run_gathers(inputs, events=events)
 

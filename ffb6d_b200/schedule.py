@@ -11,11 +11,12 @@ import contextlib
 
 import torch
 
-from .ops import knn_search, KnnGrid, knn_uses_grid
+from .ops import knn_search, KnnGrid, knn_uses_grid, subset_nn_from_knn
 
 from .tables import (RGB_DS_SR, RGB_UP_SR, PCLD_SUB_S_R, N_DS_LAYERS, N_UP_LAYERS, K_NEIGH,  # noqa: F401
                      DS_RGB_OC, DS_RNDLA_OC, UP_RGB_OC, UP_RNDLA_OC, knn_schedule, set_size, gather_schedule,
-                     fusion_mlp_schedule, knn_alg_bytes, gather_alg_bytes, frame_alg_bytes, derived_searches, derived_image_searches)
+                     fusion_mlp_schedule, knn_alg_bytes, gather_alg_bytes, frame_alg_bytes, derived_searches, derived_image_searches,
+                     derived_subset_searches)
 
 
 def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
@@ -30,8 +31,7 @@ def image_pyramid(dpt_xyz, levels=(1, 2, 4, 8)):
 
 
 def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, timer=None, streams=None,
-                        pyramid=None, image_hw=None, events=None, priority=None, build_streams=None,
-                        interleave_builds=False):
+                        pyramid=None, image_hw=None, events=None, priority=None, build_streams=None):
     """All neighbour-index tensors of the FFB6D fusion stack for a batch, on the GPU.
 
     :param cld: ``[B, N0, 3]`` float32 CUDA, the sampled (already shuffled) cloud
@@ -41,9 +41,6 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     :param streams: optional list of side ``torch.cuda.Stream`` s to overlap the 22 searches on
     :param build_streams: optional extra side streams for the grid builds (latency-bound cluster kernels that
       co-run well); the caller joins them together with ``streams``
-    :param interleave_builds: with ``streams``: build every grid right before the first search that needs it, on that
-      search's stream, instead of all grids first (the first searches -- and the gathers they unlock -- start one build
-      after the pass begins, the remaining latency-bound builds run underneath them)
     :param priority: optional ``{index key: float}``; with ``streams`` the searches (and the grid
       builds they need) are issued in descending priority instead of descending size, so that the
       searches whose consumers are expensive finish first
@@ -73,28 +70,17 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
         if image_hw is None:
             raise ValueError("image_hw=(H, W) is required with pyramid=")
         H, W = image_hw
+        sets = {("img", sr): pyramid[sr] for sr in used}
     else:
         if dpt_xyz is None or dpt_xyz.dim() != 4 or cld.shape[0] != dpt_xyz.shape[0]:
             raise ValueError("expected dpt_xyz [B,H,W,3] (or pyramid=)")
         H, W = dpt_xyz.shape[1], dpt_xyz.shape[2]
-    sets = {}
-
-    def make_image_sets():
-        if pyramid is not None:
-            sets.update({("img", sr): pyramid[sr] for sr in used})
-        else:
-            sets.update({("img", sr): p for sr, p in image_pyramid(dpt_xyz.float(), used).items()})
-
-    def make_cloud_sets():
-        n = n0
-        for i in range(N_DS_LAYERS + 1):
-            sets[("cld", i)] = cld if i == 0 else cld[:, :n, :].contiguous()
-            if i < N_DS_LAYERS:
-                n //= PCLD_SUB_S_R[i]
-
-    def size(name):
-        return set_size(name, n0, H, W)
-
+        sets = {("img", sr): p for sr, p in image_pyramid(dpt_xyz.float(), used).items()}
+    n = n0
+    for i in range(N_DS_LAYERS + 1):
+        sets[("cld", i)] = cld if i == 0 else cld[:, :n, :].contiguous()
+        if i < N_DS_LAYERS:
+            n //= PCLD_SUB_S_R[i]
     inputs = {}
     calls = knn_schedule(n0, H, W, k)
     # one grid per (point set, K class) shared by all the searches into it; supports whose
@@ -102,8 +88,17 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     groups = {}
     for key, s, q, kk in calls:
         groups.setdefault((s, kk), []).append((key, q))
+    # cld_interp_idx{i} (nearest level-(i+1) point of every level-i point) is read off cld_nei_idx{i}: level i+1 is a
+    # row prefix of level i, so the first entry of a self-search row that is < N_{i+1} is the answer; only the rows
+    # without one (0.75^K of them) are searched (ops.subset_nn_from_knn).  Worth it where the search would take the grid.
+    import os
+    derived_sub = {c: p_ for c, p_ in derived_subset_searches(calls).items()
+                   if k >= 8 and os.environ.get("FFB6D_SUBSET_NN", "0") == "1"}
+    derived_sub = {c: p_ for c, p_ in derived_sub.items()
+                   if any(key == c and knn_uses_grid(B, sets[s].shape[1], sets[q].shape[1], kk) for key, s, q, kk in calls)}
     gridded = [g for g, members in groups.items()
-               if any(knn_uses_grid(B, size(g[0]), size(q), g[1]) for _, q in members)]
+               if any(knn_uses_grid(B, sets[g[0]].shape[1], sets[q].shape[1], g[1]) for key_, q in members
+                      if key_ not in derived_sub)]
     grids = {}
     main = torch.cuda.current_stream(cld.device)
     par = streams is not None and timer is None
@@ -141,26 +136,7 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     for child, (parent, f) in derived_img.items():
         children_img.setdefault(parent, []).append((child, f))
 
-    # the strided pyramid levels and the cloud prefixes are copies: with interleave_builds they are made on the side
-    # streams (image levels on one, cloud levels on another) instead of ahead of the fork on the caller's stream
-    sets_ready = []
-    if not (par and interleave_builds):
-        make_image_sets()
-        make_cloud_sets()
     fork()
-    if par and interleave_builds:
-        for i, make in enumerate((make_image_sets, make_cloud_sets)):
-            with on(i):
-                make()
-                ev = torch.cuda.Event()
-                ev.record()
-                sets_ready.append(ev)
-
-    def wait_sets():
-        cur = torch.cuda.current_stream(cld.device)
-        for ev in sets_ready:
-            cur.wait_event(ev)
-
     # a search waits only for ITS grid, a consumer only for ITS index tensor (events, not joins)
     built = {}
     if par and priority:
@@ -170,34 +146,25 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
             first_use.setdefault((s_, kk_), pos)
         build_order = sorted(gridded, key=lambda g: first_use.get(g, len(order)))
     else:
-        order = sorted(calls, key=lambda c: -(size(c[2]) * c[3])) if par else calls
-        build_order = sorted(gridded, key=lambda g: -size(g[0]))
-    def build(g):
-        if timer is not None:
-            timer.start("knn_build:%s%d:k%d" % (g[0][0], g[0][1], g[1]), 0)
-        wait_sets()
-        grids[g] = KnnGrid(sets[g[0]], g[1])
-        if timer is not None:
-            timer.stop()
-        if par:
-            built[g] = torch.cuda.Event()
-            built[g].record()
-
-    lazy = bool(interleave_builds) and par
-    if not lazy:
-        for i, g in enumerate(build_order):
-            with on(i, bstreams or None):
-                build(g)
-    order = [c for c in order if c[0] not in derived and c[0] not in derived_img]
-    qsize = {key: size(q) for key, s, q, kk in calls}
+        order = sorted(calls, key=lambda c: -(sets[c[2]].shape[1] * c[3])) if par else calls
+        build_order = sorted(gridded, key=lambda g: -sets[g[0]].shape[1])
+    for i, g in enumerate(build_order):
+        with on(i, bstreams or None):
+            if timer is not None:
+                timer.start("knn_build:%s%d:k%d" % (g[0][0], g[0][1], g[1]), 0)
+            grids[g] = KnnGrid(sets[g[0]], g[1])
+            if timer is not None:
+                timer.stop()
+            if par:
+                built[g] = torch.cuda.Event()
+                built[g].record()
+    order = [c for c in order if c[0] not in derived and c[0] not in derived_img and c[0] not in derived_sub]
+    qsize = {key: sets[q].shape[1] for key, s, q, kk in calls}
     for i, (key, s, q, kk) in enumerate(order):
+        sup, qry = sets[s], sets[q]
         with on(i):
-            wait_sets()
-            sup, qry = sets[s], sets[q]
             if timer is not None:
                 timer.start("knn:" + key, knn_alg_bytes(sup.shape[1], qry.shape[1], kk) * B)
-            if lazy and (s, kk) in gridded and (s, kk) not in grids:
-                build((s, kk))          # first use: same stream, no event wait needed
             if (s, kk) in grids:
                 if par:
                     torch.cuda.current_stream(cld.device).wait_event(built[(s, kk)])
@@ -214,6 +181,15 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
                 n_sub = sets[("cld", lvl + 1)].shape[1]
                 inputs["cld_sub_idx%d" % lvl] = inputs[key][:, :n_sub, :].contiguous()
                 done.append("cld_sub_idx%d" % lvl)
+                child = "cld_interp_idx%d" % lvl
+                if derived_sub.get(child) == key:
+                    sub = sets[("cld", lvl + 1)]
+                    if timer is not None:
+                        timer.start("knn:" + child, knn_alg_bytes(sub.shape[1], qry.shape[1], 1) * B)
+                    inputs[child] = subset_nn_from_knn(sub, qry, inputs[key])
+                    if timer is not None:
+                        timer.stop()
+                    done.append(child)
             for child in children.get(key, ()):   # prefix slices instead of separate searches (see above)
                 inputs[child] = inputs[key][:, :qsize[child], :].contiguous()
                 done.append(child)
@@ -235,8 +211,6 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
         join()
     for i in range(N_DS_LAYERS):
         inputs["cld_xyz%d" % i] = sets[("cld", i)]
-        if sets_ready and i > 0 and not torch.cuda.is_current_stream_capturing():
-            sets[("cld", i)].record_stream(main)     # made on a side stream, handed to the caller's stream
     return inputs
 
 

@@ -61,14 +61,22 @@ class Split:
         return inputs, outs
 
 
+def mk(**kw):
+    return lambda: FusionPass(B, device=dev, **kw)
+
+
+def with_env(make, **env):
+    def f():
+        os.environ.update({k: str(v) for k, v in env.items()})     # read by the scheduler while the variant is captured
+        return make()
+    return f
+
+
 variants = {
-    "base": lambda: FusionPass(B, device=dev, choose_first=False, interleave_builds=False),
-    "choose_first": lambda: FusionPass(B, device=dev, choose_first=True, interleave_builds=False),
-    "lazy_builds": lambda: FusionPass(B, device=dev, choose_first=False, interleave_builds=True),
-    "both": lambda: FusionPass(B, device=dev, choose_first=True, interleave_builds=True),
-    "both_g3": lambda: FusionPass(B, device=dev, choose_first=True, interleave_builds=True, n_gather_streams=3),
-    "both_s3": lambda: FusionPass(B, device=dev, choose_first=True, interleave_builds=True, n_streams=3, n_gather_streams=2),
-    "split2_both": lambda: Split(2, choose_first=True, interleave_builds=True),
+    "base": with_env(mk(), FFB6D_SUBSET_NN=0, FFB6D_SELF_FIRST=1),
+    "subset_nn": with_env(mk(), FFB6D_SUBSET_NN=1, FFB6D_SELF_FIRST=1),
+    "subset_nn_noselffirst": with_env(mk(), FFB6D_SUBSET_NN=1, FFB6D_SELF_FIRST=0),
+    "noselffirst": with_env(mk(), FFB6D_SUBSET_NN=0, FFB6D_SELF_FIRST=0),
 }
 if only:
     variants = {k: v for k, v in variants.items() if k in only}
@@ -78,8 +86,8 @@ ref = digest(*seq(cld, xyz, cho))
 del seq
 print("sequential digest", ref, flush=True)
 runs = {}
-for name, mk in variants.items():
-    p = mk()
+for name, make in variants.items():
+    p = make()
     for _ in range(3):
         p(cld, xyz, cho)
     torch.cuda.synchronize()
