@@ -8,6 +8,7 @@ runs the index build on the GPU for a whole batch: xyz goes in, the same dict
 keys with the same shapes and dtypes (int32) come out, already on the device.
 """
 import contextlib
+import os
 
 import torch
 
@@ -88,10 +89,10 @@ def build_ffb6d_indices(cld, dpt_xyz=None, k=K_NEIGH, index_dtype=torch.int32, t
     groups = {}
     for key, s, q, kk in calls:
         groups.setdefault((s, kk), []).append((key, q))
-    # cld_interp_idx{i} (nearest level-(i+1) point of every level-i point) is read off cld_nei_idx{i}: level i+1 is a
-    # row prefix of level i, so the first entry of a self-search row that is < N_{i+1} is the answer; only the rows
-    # without one (0.75^K of them) are searched (ops.subset_nn_from_knn).  Worth it where the search would take the grid.
-    import os
+    # FFB6D_SUBSET_NN=1 (off by default: exact, but the pass is slower with it): cld_interp_idx{i}
+    # (nearest level-(i+1) point of every level-i point) is read off cld_nei_idx{i} -- level i+1 is a row prefix of
+    # level i, so the first entry of a self-search row that is < N_{i+1} is the answer; only the rows without one
+    # (0.75^K of them) are searched (ops.subset_nn_from_knn).  Applies where the search would take the grid.
     derived_sub = {c: p_ for c, p_ in derived_subset_searches(calls).items()
                    if k >= 8 and os.environ.get("FFB6D_SUBSET_NN", "0") == "1"}
     derived_sub = {c: p_ for c, p_ in derived_sub.items()
