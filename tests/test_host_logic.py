@@ -97,3 +97,17 @@ def test_synthetic_backprojection_is_the_references():
         fr = synthetic.make_frame(case["seed"], n_points=768, intrinsics=case["intrinsics"])
         assert hashlib.sha256(np.ascontiguousarray(fr["depth"]).tobytes()).hexdigest() == case["sha256_depth"]
         assert hashlib.sha256(np.ascontiguousarray(fr["dpt_xyz"]).tobytes()).hexdigest() == case["sha256_xyz_f32"]
+
+
+def test_tile_kernel_reciprocal_division_is_exact():
+    """grid_search_k1_tile_kernel (csrc/knn_grid.cu) replaces `tile / tiles_x` and `lane / by` by
+    `(int)((i + 0.5f) * (1.0f / n))` whenever `tiles + tiles_x < 4 000 000` (the launcher passes `exact_div` otherwise).
+    numpy float32 performs the same IEEE round-to-nearest operations: the identity holds on the whole admitted range."""
+    for n in list(range(1, 48)) + [80, 160, 320, 333, 640, 1000, 4096, 65535, 1000003, 3999999]:
+        t = np.arange(0, 4000000 - n, dtype=np.int64)
+        got = ((t.astype(np.float32) + np.float32(0.5)) * (np.float32(1.0) / np.float32(n))).astype(np.int64)
+        assert np.array_equal(got, t // n), n
+    lanes = np.arange(32)
+    for by in range(1, 33):
+        got = ((lanes.astype(np.float32) + np.float32(0.5)) * (np.float32(1.0) / np.float32(by))).astype(np.int64)
+        assert np.array_equal(got, lanes // by), by
