@@ -55,21 +55,6 @@ def test_no_strided_derivation_for_indivisible_images():
     assert set(d) == {"p2r_ds_nei_idx0"}
 
 
-def _subset_nn_from_knn(knn, n_sub, support, query):
-    """numpy statement of ``ffb6d_knn_subset_nn``: first row entry below ``n_sub``, else a search."""
-    out = np.empty((len(knn), 1), knn.dtype)
-    missed = []
-    for q, row in enumerate(knn):
-        hit = row[row < n_sub]
-        if len(hit):
-            out[q, 0] = hit[0]
-        else:
-            missed.append(q)
-    if missed:
-        out[missed] = O.knn_search(support[None], query[missed][None], 1)[0]
-    return out, len(missed)
-
-
 def test_nearest_next_level_point_is_read_off_the_self_search():
     """cld_interp_idx{i} == first entry of each cld_nei_idx{i} row that lies in level i+1 (a row prefix); rows without
     one are searched.  Checked against the oracle's own K = 1 searches, on a plain frame, on a frame with duplicated
@@ -89,7 +74,7 @@ def test_nearest_next_level_point_is_read_off_the_self_search():
             n_sub = sets[s_c].shape[0]
             assert np.array_equal(sets[s_c], sets[q_c][:n_sub])               # the support IS a row prefix of the queries
             knn = O.knn_search(sets[q_c][None], sets[q_c][None], min(k_list, len(sets[q_c])))[0]
-            got, missed = _subset_nn_from_knn(knn, n_sub, sets[s_c], sets[q_c])
+            got, missed = O.subset_nn_from_knn(knn, n_sub, sets[s_c], sets[q_c])
             want = O.knn_search(sets[s_c][None], sets[q_c][None], 1)[0]
             assert np.array_equal(got, want), (child, k_list)
             if k_list == 3 and len(sets[q_c]) >= 768:
